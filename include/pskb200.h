@@ -1,0 +1,221 @@
+/* pskb200.h -- C ABI of the B200-native run-length-encoded array evaluation path.
+ *
+ * This is the drop-in boundary for ONE hot path of turtlesoupy/pyskip: evaluation of
+ * run-end encoded arrays (k-way merge of run ends + fused element-wise program per output
+ * span + equal-run compaction, through strided / masked N-D views, plus dense<->RLE
+ * conversion and reductions).  The reference has no FFI seam of its own: the call that
+ * this library replaces is
+ *
+ *     eval::eval_simple<Ret, Box, StepFn, k>(EvalFn, SimplePool)
+ *         include/pyskip/detail/eval.hpp:632-659, called from
+ *     lang::execute_plan_fixed            include/pyskip/detail/lang.hpp:749-784
+ *
+ * whose inputs are an EvalPlan (lang.hpp:602-614: postfix program of SOURCE | MERGE_n) and
+ * per source a (store, start, stop, step_fn) tuple (lang.hpp:696-743).  Because a MergeFn
+ * is an opaque host function pointer (lang.hpp:56) the program crosses this ABI as
+ * op-codes, and because a cyclic::StepFn is a host LUT tree (detail/step.hpp:35-172) a
+ * view crosses it as a closed-form strided-box descriptor.
+ *
+ * Conventions
+ *   - plain C types only; no C++ exceptions cross the ABI; no torch types.
+ *   - every entry point returns a psk_status; psk_last_error() gives the thread-local
+ *     message.  PSK_EINVAL <-> std::invalid_argument (CHECK_ARGUMENT, detail/errors.hpp:7-13),
+ *     PSK_ESTATE <-> std::logic_error (CHECK_STATE, errors.hpp:15-21).
+ *   - stores are immutable, reference counted, and live in device memory (HBM) as two
+ *     arrays: int32 ends[nruns] (strictly increasing exclusive run ends, ends[nruns-1] ==
+ *     span) and uint32 vals[nruns] (32-bit payload: int32, float32 bits, bool 0/1, char
+ *     sign-extended) -- the layout of core::Store (detail/core.hpp:12-62) with the Box
+ *     (detail/box.hpp:11-127) flattened to its 4 information bytes.
+ *   - all work is issued on one library stream per process; calls that return data to the
+ *     host synchronise that stream, everything else is asynchronous.
+ *   - there is NO CPU implementation behind this ABI.  Without a CUDA device every compute
+ *     entry point fails with PSK_ECUDA.
+ */
+#ifndef PSKB200_H_
+#define PSKB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define PSK_API
+#else
+#define PSK_API __attribute__((visibility("default")))
+#endif
+
+typedef int32_t psk_status;
+enum {
+  PSK_OK = 0,
+  PSK_EINVAL = 1,  /* bad argument            (reference: std::invalid_argument) */
+  PSK_ESTATE = 2,  /* broken invariant        (reference: std::logic_error)      */
+  PSK_ECUDA = 3,   /* CUDA runtime / driver error, or no device                  */
+  PSK_ENOMEM = 4
+};
+
+/* Element types bound by the reference (src/cpp_ext/binds/*_binds.cpp:3-5). */
+typedef enum { PSK_I32 = 0, PSK_F32 = 1, PSK_BOOL = 2, PSK_CHAR = 3 } psk_dtype;
+
+/* Equality used by run compaction:
+ *   BITWISE: Box::operator== on the 32-bit payload (detail/box.hpp:84-90) -- Array.eval(),
+ *            every intermediate materialisation (lang.hpp:890, 902-905);
+ *   TYPED  : C++ operator== on the value type (float: NaN != NaN, -0 == +0) -- the final
+ *            step of store()/runs()/to_numpy()/get() (lang.hpp:899) and from_buffer
+ *            (detail/conv.hpp:21-25).                                                  */
+typedef enum { PSK_EQ_BITWISE = 0, PSK_EQ_TYPED = 1 } psk_eq;
+
+typedef struct psk_store_s* psk_store_t; /* opaque, reference counted */
+
+/* ---- views: closed forms of the reference's step functions --------------------------
+ * A strided box over a flat array of `shape` (dim 0 fastest, tensor.hpp:102-121) selects
+ * positions sel(0) < ... < sel(m-1) (x_d in {start_d, start_d+stride_d, ...} below stop_d).
+ *   GATHER : run end E of the source lands at f(E) = |{ j : sel(j) < E }|
+ *            (TensorSlice::get_fn tensor.hpp:99-125, Slice::get_fn array.hpp:54-56)
+ *   SCATTER: run end E of the (small) source lands at g(E): g(0)=0, g(E)=sel(E), g(m)=n
+ *            (TensorSlice::set_fn tensor.hpp:127-169, cyclic::insert_fn step.hpp:583-598)
+ *   AFFINE : f(E) = offset + scale*E for 0 < E <= span_in (cyclic::scaled/shift,
+ *            step.hpp:319-355); shape[0]=span_in, start[0]=scale, stop[0]=offset.
+ * A source carries a chain of up to PSK_MAX_VIEWS views applied innermost (views[0])
+ * first (lang::slice_eval, lang.hpp:37-42).                                            */
+#define PSK_MAX_DIM 4
+#define PSK_MAX_VIEWS 4
+#define PSK_MAX_SOURCES 32   /* lang::execute_plan switch, lang.hpp:790-857 */
+#define PSK_MAX_PROGRAM 192
+
+typedef enum { PSK_VIEW_GATHER = 1, PSK_VIEW_SCATTER = 2, PSK_VIEW_AFFINE = 3 } psk_view_kind;
+
+typedef struct {
+  int32_t kind; /* psk_view_kind */
+  int32_t ndim; /* 1..PSK_MAX_DIM */
+  int32_t shape[PSK_MAX_DIM];
+  int32_t start[PSK_MAX_DIM];
+  int32_t stop[PSK_MAX_DIM];
+  int32_t stride[PSK_MAX_DIM];
+} psk_view;
+
+typedef struct {
+  psk_store_t store;
+  int32_t nviews;
+  psk_view views[PSK_MAX_VIEWS];
+} psk_source;
+
+/* ---- fused element-wise program: postfix, one node per EvalPlan::Node (lang.hpp:602-614).
+ * Op-codes cover the operator catalogue of include/pyskip/array.hpp:276-338.  The _I
+ * family works on int32 payloads (also bool 0/1 and char), the _F family on float32.  */
+typedef enum {
+  PSK_OP_SRC = 0,   /* push current value of source `arg`                       */
+  PSK_OP_CONST = 1, /* push the 32-bit immediate `arg` (a 1-run broadcast scalar,
+                       macros.hpp:16-23, folded by the planner)                  */
+  /* int32 */
+  PSK_OP_ADD_I = 10, PSK_OP_SUB_I, PSK_OP_MUL_I, PSK_OP_DIV_I, PSK_OP_MOD_I, PSK_OP_NEG_I,
+  PSK_OP_ABS_I, PSK_OP_BNOT_I, PSK_OP_AND_I, PSK_OP_OR_I, PSK_OP_XOR_I, PSK_OP_SHL_I,
+  PSK_OP_SHR_I, PSK_OP_MIN_I, PSK_OP_MAX_I, PSK_OP_POW_I, PSK_OP_SQRT_I, PSK_OP_EXP_I,
+  PSK_OP_COALESCE_I, PSK_OP_EQ_I, PSK_OP_NE_I, PSK_OP_LT_I, PSK_OP_GT_I, PSK_OP_LE_I,
+  PSK_OP_GE_I, PSK_OP_LNOT_I, PSK_OP_LAND_I, PSK_OP_LOR_I,
+  /* float32 (IEEE binary32, round to nearest, no contraction) */
+  PSK_OP_ADD_F = 50, PSK_OP_SUB_F, PSK_OP_MUL_F, PSK_OP_DIV_F, PSK_OP_MOD_F, PSK_OP_NEG_F,
+  PSK_OP_ABS_F, PSK_OP_MIN_F, PSK_OP_MAX_F, PSK_OP_POW_F, PSK_OP_SQRT_F, PSK_OP_EXP_F,
+  PSK_OP_COALESCE_F, PSK_OP_EQ_F, PSK_OP_NE_F, PSK_OP_LT_F, PSK_OP_GT_F, PSK_OP_LE_F,
+  PSK_OP_GE_F, PSK_OP_LNOT_F, PSK_OP_LAND_F, PSK_OP_LOR_F,
+  /* type agnostic */
+  PSK_OP_SELECT = 80, /* (m, a, b) -> m ? a : b   (splat, array.hpp:323-325)   */
+  /* casts (array.hpp:277-281) */
+  PSK_OP_I2F = 90, PSK_OP_F2I, PSK_OP_I2B, PSK_OP_F2B, PSK_OP_I2C, PSK_OP_F2C
+} psk_opcode;
+
+typedef struct {
+  int32_t op;   /* psk_opcode */
+  uint32_t arg; /* source index or immediate */
+} psk_node;
+
+typedef enum { PSK_RED_SUM = 0, PSK_RED_MAX = 1, PSK_RED_MIN = 2, PSK_RED_PROD = 3 } psk_reduce_op;
+
+/* ---- library / device ------------------------------------------------------------- */
+PSK_API const char* psk_last_error(void);
+PSK_API const char* psk_version(void);
+/* 0 for the CUDA library.  (The test-only kernel simulator under tests/sim reports 1;
+ * the package never loads it.) */
+PSK_API int32_t psk_is_simulator(void);
+/* Bind this process to CUDA device `device` and create the library stream. */
+PSK_API psk_status psk_init(int32_t device);
+PSK_API psk_status psk_device_count(int32_t* count);
+PSK_API psk_status psk_synchronize(void);
+/* Raw cudaStream_t of the library stream (for event timing / interop). */
+PSK_API psk_status psk_get_stream(void** stream);
+/* Device-side timer on the library stream (CUDA events). */
+PSK_API psk_status psk_timer_start(void);
+PSK_API psk_status psk_timer_stop(float* elapsed_ms);
+/* Number of kernels this library launched since the last reset (bench gpu_launches). */
+PSK_API int64_t psk_launch_count(int32_t reset);
+/* Bytes currently held by live stores. */
+PSK_API int64_t psk_live_bytes(void);
+
+/* ---- stores: core::Store (detail/core.hpp:12-62) ----------------------------------- */
+/* From host run arrays (core::Store ctor; validated: n>0, ends strictly increasing). */
+PSK_API psk_status psk_store_from_runs(psk_dtype dtype, int64_t nruns, const int32_t* ends,
+                                       const void* vals, psk_store_t* out);
+/* Same, from device arrays (copied device-to-device on the library stream). */
+PSK_API psk_status psk_store_from_device_runs(psk_dtype dtype, int64_t nruns,
+                                              const int32_t* d_ends, const uint32_t* d_vals,
+                                              psk_store_t* out);
+/* core::make_store(span, fill) (core.hpp:104-111): one run. */
+PSK_API psk_status psk_store_fill(psk_dtype dtype, int32_t span, uint32_t fill_bits,
+                                  psk_store_t* out);
+/* conv::to_store (detail/conv.hpp:15-44): dense host buffer (element size 4 for
+ * I32/F32, 1 for BOOL/CHAR) -> canonical RLE under TYPED equality, encoded on device. */
+PSK_API psk_status psk_store_from_dense(psk_dtype dtype, int64_t n, const void* dense,
+                                        psk_store_t* out);
+PSK_API psk_status psk_store_from_dense_device(psk_dtype dtype, int64_t n,
+                                               const void* d_dense, psk_store_t* out);
+/* conv::to_buffer (detail/conv.hpp:63-78): expand on device, copy to host. */
+PSK_API psk_status psk_store_to_dense(psk_store_t s, void* out_host);
+PSK_API psk_status psk_store_to_dense_device(psk_store_t s, void* d_out);
+/* Array.runs() (type_binds.hpp:145-151): copy (ends, vals) to host. */
+PSK_API psk_status psk_store_runs(psk_store_t s, int32_t* ends, void* vals);
+PSK_API int64_t psk_store_nruns(psk_store_t s);
+PSK_API int32_t psk_store_span(psk_store_t s);
+PSK_API int32_t psk_store_dtype(psk_store_t s);
+/* Device pointers of the run arrays (valid while the store is alive). */
+PSK_API psk_status psk_store_device_ptrs(psk_store_t s, const int32_t** d_ends,
+                                         const uint32_t** d_vals);
+/* The payload of run 0 (used for 1-run stores, i.e. scalars). */
+PSK_API psk_status psk_store_first_value(psk_store_t s, uint32_t* bits);
+PSK_API void psk_store_retain(psk_store_t s);
+PSK_API void psk_store_release(psk_store_t s);
+
+/* ---- the hot path: eval::eval_simple (detail/eval.hpp:632-659) ---------------------- */
+/* Evaluate `prog` over `k` sources that share one output span; the result is the
+ * canonical RLE under `eq` (equal neighbours merge, the later value is kept:
+ * eval.hpp:189-202, :581-588).  out_dtype tags the result. */
+PSK_API psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog,
+                            const psk_node* prog, psk_dtype out_dtype, psk_eq eq,
+                            psk_store_t* out);
+/* Output span of a source view chain applied to a store span (lang::slice, lang.hpp:162). */
+PSK_API psk_status psk_view_span(int32_t span_in, int32_t nviews, const psk_view* views,
+                                 int32_t* span_out);
+
+/* ---- masks: TensorSlice::mask / mask::stride_mask (tensor.hpp:171-198, mask.hpp:184-200)
+ * RLE indicator (BOOL) of the positions a strided box selects, generated on device. */
+PSK_API psk_status psk_mask_nd(int32_t ndim, const int32_t* shape, const int32_t* start,
+                               const int32_t* stop, const int32_t* stride, psk_store_t* out);
+
+/* ---- reductions (src/pyskip/reduce.py:8-50 collapsed to one pass over runs) ---------
+ * SUM: sum(val*len) -- int32 wraps mod 2^32 (result_bits low 32), float32 accumulates in
+ * fp64 and returns the fp64 bits; MAX/MIN over run values; PROD = prod(val^len) (int32
+ * wrap / fp64). */
+PSK_API psk_status psk_reduce(psk_store_t s, psk_reduce_op op, uint64_t* result_bits);
+
+/* ---- multi-GPU helpers (fuse_stores boundary rule, detail/eval.hpp:568-607) ----------
+ * A shard's first/last payloads and run count, for the stitch all-gather. */
+PSK_API psk_status psk_store_boundary(psk_store_t s, uint32_t* first_bits, uint32_t* last_bits,
+                                      int64_t* nruns);
+/* Sub-range [start, stop) of a store re-based to 0 (SimpleSource::split, eval.hpp:281-287). */
+PSK_API psk_status psk_store_slice(psk_store_t s, int32_t start, int32_t stop, psk_store_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSKB200_H_ */

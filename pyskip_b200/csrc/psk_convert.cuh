@@ -1,0 +1,297 @@
+// psk_convert.cuh -- dense <-> RLE conversion, mask generation and reductions over runs.
+//
+//   encode  : conv::to_store   include/pyskip/detail/conv.hpp:15-44  (two passes over the
+//             dense buffer on one CPU thread) -> count / scan / write kernels.
+//   expand  : conv::to_buffer  detail/conv.hpp:63-78                -> one kernel.
+//   mask    : mask::build      detail/mask.hpp:132-182 driven by TensorSlice::mask
+//             (tensor.hpp:171-198) -> one kernel emits the raw (segment) run list, the eval
+//             kernel canonicalises it.
+//   reduce  : src/pyskip/reduce.py:8-50 (log2(n) strided 2-source evals) collapses to one
+//             pass over the runs: sum(val * len), max, min, prod.
+#pragma once
+
+#include "psk_ops.h"
+#include "psk_plan.h"
+
+namespace psk {
+
+constexpr int kConvThreads = 256;
+constexpr int kConvItems = 8;
+constexpr int kConvChunk = kConvThreads * kConvItems;  // dense elements per block
+
+// dense element -> 32-bit payload
+template <int DT>
+PSK_D uint32_t load_payload(const void* dense, long long i) {
+  if (DT == PSK_I32 || DT == PSK_F32) return reinterpret_cast<const uint32_t*>(dense)[i];
+  if (DT == PSK_BOOL) return reinterpret_cast<const uint8_t*>(dense)[i] ? 1u : 0u;
+  return (uint32_t)(int32_t) reinterpret_cast<const int8_t*>(dense)[i];
+}
+template <int DT>
+PSK_D void store_payload(void* dense, long long i, uint32_t v) {
+  if (DT == PSK_I32 || DT == PSK_F32) reinterpret_cast<uint32_t*>(dense)[i] = v;
+  else reinterpret_cast<uint8_t*>(dense)[i] = (uint8_t)v;
+}
+// conv.hpp:21-25: typed `buffer[i] != buffer[i-1]`
+template <int DT>
+PSK_D bool typed_differs(uint32_t a, uint32_t b) {
+  if (DT == PSK_F32) return u2f(a) != u2f(b);
+  return a != b;
+}
+
+// element i closes a run iff it is the last element or differs from element i+1
+template <int DT>
+__global__ void __launch_bounds__(kConvThreads) k_encode_count(const void* dense, long long n,
+                                                               int32_t* block_count) {
+  __shared__ int32_t s_warp[kConvThreads / 32];
+  const long long base = (long long)blockIdx.x * kConvChunk;
+  int32_t c = 0;
+#pragma unroll
+  for (int it = 0; it < kConvItems; ++it) {
+    long long i = base + it * kConvThreads + threadIdx.x;
+    if (i < n) {
+      bool b = (i == n - 1) || typed_differs<DT>(load_payload<DT>(dense, i), load_payload<DT>(dense, i + 1));
+      c += b ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t t = 0;
+    for (int w = 0; w < kConvThreads / 32; ++w) t += s_warp[w];
+    block_count[blockIdx.x] = t;
+  }
+}
+
+// single-block exclusive scan of nb counts; total -> *total_out
+__global__ void __launch_bounds__(1024) k_scan_counts(int32_t* counts, int32_t nb, int32_t* total_out) {
+  __shared__ int32_t s_warp[33];
+  __shared__ int32_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int32_t base = 0; base < nb; base += 1024) {
+    int32_t i = base + threadIdx.x;
+    int32_t v = i < nb ? counts[i] : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      int32_t w = s_warp[lane];
+      int32_t winc = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int32_t o = __shfl_up_sync(0xffffffffu, winc, d);
+        if (lane >= d) winc += o;
+      }
+      s_warp[lane] = winc - w;
+      if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    const int32_t carry = s_carry;
+    if (i < nb) counts[i] = carry + s_warp[warp] + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + s_warp[32];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = s_carry;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kConvThreads) k_encode_write(const void* dense, long long n,
+                                                               const int32_t* block_off,
+                                                               int32_t* ends, uint32_t* vals) {
+  __shared__ int32_t s_warp[kConvThreads / 32 + 1];
+  const long long base = (long long)blockIdx.x * kConvChunk;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int32_t running = block_off[blockIdx.x];
+  for (int it = 0; it < kConvItems; ++it) {
+    long long i = base + it * kConvThreads + threadIdx.x;
+    bool b = false;
+    uint32_t v = 0;
+    if (i < n) {
+      v = load_payload<DT>(dense, i);
+      b = (i == n - 1) || typed_differs<DT>(v, load_payload<DT>(dense, i + 1));
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, b);
+    int32_t wcount = __popc(bal);
+    int32_t wpos = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) s_warp[warp] = wcount;
+    __syncthreads();
+    int32_t woff = 0, tot = 0;
+    for (int w = 0; w < kConvThreads / 32; ++w) {
+      int32_t cw = s_warp[w];
+      if (w < warp) woff += cw;
+      tot += cw;
+    }
+    if (b) {
+      ends[running + woff + wpos] = (int32_t)(i + 1);
+      vals[running + woff + wpos] = v;
+    }
+    running += tot;
+    __syncthreads();
+  }
+}
+
+// expand: each block writes kConvChunk consecutive dense elements
+template <int DT>
+__global__ void __launch_bounds__(kConvThreads) k_expand(const int32_t* ends, const uint32_t* vals,
+                                                         int32_t nruns, long long n, void* dense) {
+  __shared__ int32_t s_ends[kConvChunk + 1];
+  __shared__ int32_t s_r0, s_nr;
+  const long long b0 = (long long)blockIdx.x * kConvChunk;
+  long long b1 = b0 + kConvChunk;
+  if (b1 > n) b1 = n;
+  if (threadIdx.x < 2) {
+    // first run whose end is > pos (core::Store::index, core.hpp:49-52)
+    int32_t pos = threadIdx.x == 0 ? (int32_t)b0 : (int32_t)(b1 - 1);
+    int32_t lo = 0, hi = nruns;
+    while (lo < hi) {
+      int32_t mid = lo + ((hi - lo) >> 1);
+      if (ends[mid] <= pos) lo = mid + 1; else hi = mid;
+    }
+    if (threadIdx.x == 0) s_r0 = lo; else s_nr = lo;
+  }
+  __syncthreads();
+  const int32_t r0 = s_r0;
+  const int32_t nr = s_nr - r0 + 1;  // <= elements in the chunk
+  for (int32_t j = threadIdx.x; j < nr; j += kConvThreads) s_ends[j] = ends[r0 + j];
+  __syncthreads();
+  for (int it = 0; it < kConvItems; ++it) {
+    long long i = b0 + it * kConvThreads + threadIdx.x;
+    if (i < b1) {
+      int32_t lo = 0, hi = nr - 1;
+      while (lo < hi) {
+        int32_t mid = (lo + hi) >> 1;
+        if (s_ends[mid] <= (int32_t)i) lo = mid + 1; else hi = mid;
+      }
+      store_payload<DT>(dense, i, vals[r0 + lo]);
+    }
+  }
+}
+
+// position of the j-th selected element of a strided box
+PSK_HD uint32_t sel_pos(const DView& v, uint32_t j) {
+  uint32_t flat = 0, rem = j;
+  for (int d = 0; d < v.ndim; ++d) {
+    uint32_t q = rem % v.cnt[d];
+    rem /= v.cnt[d];
+    flat += (v.c0[d] + q * v.cs[d]) * v.scale[d];
+  }
+  return flat;
+}
+
+// raw run list of a box mask: per segment (a dim-0 row when stride_0 == 1, else one
+// element) an excluded run ending at its start and an included run ending at its end
+__global__ void k_mask_segments(DView v, uint32_t seg_len, int32_t nseg, int32_t* ends, uint32_t* vals) {
+  int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < nseg) {
+    uint32_t start = sel_pos(v, (uint32_t)s * seg_len);
+    ends[2 * s] = (int32_t)start;
+    vals[2 * s] = 0;
+    ends[2 * s + 1] = (int32_t)(start + seg_len);
+    vals[2 * s + 1] = 1;
+  }
+  if (s == 0) {
+    ends[2 * nseg] = (int32_t)v.n;
+    vals[2 * nseg] = 0;
+  }
+}
+
+// ---- reductions over runs ---------------------------------------------------------------
+constexpr int kRedThreads = 256;
+constexpr int kRedBlocks = 1184;  // 8 x 148 SMs
+
+struct RedAcc {
+  uint32_t isum;  // int32 sum / product, wraps mod 2^32
+  double fsum;    // float sum / product in fp64
+  uint32_t mx, mn;
+  int32_t any;
+};
+
+PSK_D uint32_t ipow_wrap(uint32_t b, uint32_t e) {
+  uint32_t r = 1;
+  while (e) {
+    if (e & 1) r *= b;
+    b *= b;
+    e >>= 1;
+  }
+  return r;
+}
+
+template <bool IS_F>
+PSK_D void red_merge(RedAcc& a, const RedAcc& b, int op) {
+  if (!b.any) return;
+  if (!a.any) { a = b; return; }
+  if (op == PSK_RED_PROD) { a.isum *= b.isum; a.fsum *= b.fsum; }
+  else { a.isum += b.isum; a.fsum += b.fsum; }
+  if (IS_F) {
+    if (u2f(a.mx) < u2f(b.mx)) a.mx = b.mx;
+    if (u2f(b.mn) < u2f(a.mn)) a.mn = b.mn;
+  } else {
+    if ((int32_t)a.mx < (int32_t)b.mx) a.mx = b.mx;
+    if ((int32_t)b.mn < (int32_t)a.mn) a.mn = b.mn;
+  }
+}
+
+template <bool IS_F>
+__global__ void __launch_bounds__(kRedThreads) k_reduce_partial(const int32_t* ends, const uint32_t* vals,
+                                                                int32_t nruns, int op, RedAcc* partial) {
+  __shared__ RedAcc s_acc[kRedThreads];
+  RedAcc acc;
+  acc.any = 0; acc.isum = 0; acc.fsum = 0; acc.mx = 0; acc.mn = 0;
+  for (int32_t i = blockIdx.x * kRedThreads + threadIdx.x; i < nruns; i += gridDim.x * kRedThreads) {
+    uint32_t len = (uint32_t)(ends[i] - (i ? ends[i - 1] : 0));
+    uint32_t v = vals[i];
+    RedAcc r;
+    r.any = 1; r.mx = v; r.mn = v;
+    if (op == PSK_RED_PROD) {
+      r.isum = ipow_wrap(v, len);
+      r.fsum = IS_F ? pow((double)u2f(v), (double)len) : 0.0;
+    } else {
+      r.isum = v * len;
+      r.fsum = IS_F ? (double)u2f(v) * (double)len : 0.0;
+    }
+    red_merge<IS_F>(acc, r, op);
+  }
+  s_acc[threadIdx.x] = acc;
+  __syncthreads();
+  for (int d = kRedThreads / 2; d > 0; d >>= 1) {
+    if ((int)threadIdx.x < d) {
+      RedAcc a = s_acc[threadIdx.x];
+      red_merge<IS_F>(a, s_acc[threadIdx.x + d], op);
+      s_acc[threadIdx.x] = a;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = s_acc[0];
+}
+
+template <bool IS_F>
+__global__ void __launch_bounds__(kRedThreads) k_reduce_final(const RedAcc* partial, int32_t nparts, int op,
+                                                              RedAcc* out) {
+  __shared__ RedAcc s_acc[kRedThreads];
+  RedAcc acc;
+  acc.any = 0; acc.isum = 0; acc.fsum = 0; acc.mx = 0; acc.mn = 0;
+  // fixed association order -> bit-reproducible fp64 sums
+  for (int32_t i = threadIdx.x; i < nparts; i += kRedThreads) red_merge<IS_F>(acc, partial[i], op);
+  s_acc[threadIdx.x] = acc;
+  __syncthreads();
+  for (int d = kRedThreads / 2; d > 0; d >>= 1) {
+    if ((int)threadIdx.x < d) {
+      RedAcc a = s_acc[threadIdx.x];
+      red_merge<IS_F>(a, s_acc[threadIdx.x + d], op);
+      s_acc[threadIdx.x] = a;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = s_acc[0];
+}
+
+}  // namespace psk

@@ -1,0 +1,823 @@
+// pskb200_abi.cu -- implementation of include/pskb200.h: store management, plan upload and
+// kernel launches for the run-length-encoded array evaluation path on one B200.
+//
+// Host-side counterpart of eval::eval_generic / eval_simple (include/pyskip/detail/eval.hpp:
+// 609-659): where the reference allocates a worst-case Store, partitions the pool over CPU
+// threads and fuses the partial stores, this file allocates the worst-case device arrays,
+// uploads a DPlan and launches k_prepare / k_sample_rank / k_tile_bounds / k_merge_eval on
+// the library stream.  There is no CPU compute path in this file.
+#include <atomic>
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "psk_convert.cuh"
+#include "psk_eval.cuh"
+
+using namespace psk;
+
+struct psk_store_s {
+  std::atomic<int> ref{1};
+  int32_t dtype = 0;
+  int64_t nruns = 0;
+  int64_t capacity = 0;
+  int32_t span = 0;
+  int32_t* d_ends = nullptr;
+  uint32_t* d_vals = nullptr;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+struct Ctx {
+  bool inited = false;
+  int device = -1;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DPlan* h_plan = nullptr;      // pinned staging copy of the plan
+  int32_t* h_ctrl = nullptr;    // pinned read-back of CTRL words / small results
+  std::atomic<int64_t> launches{0};
+  std::atomic<int64_t> live_bytes{0};
+  std::mutex mu;
+  std::recursive_mutex api_mu;  // entry points serialise on the single library stream
+};
+Ctx g;
+
+psk_status fail(psk_status code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define PSK_CHECK_ARG(cond)                                                              \
+  do {                                                                                   \
+    if (!(cond)) return fail(PSK_EINVAL, std::string("invalid argument: ") + #cond);     \
+  } while (0)
+#define PSK_CHECK_STATE(cond)                                                            \
+  do {                                                                                   \
+    if (!(cond)) return fail(PSK_ESTATE, std::string("invalid state: ") + #cond);        \
+  } while (0)
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(PSK_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+#define NEED_INIT()                                                                      \
+  std::lock_guard<std::recursive_mutex> api_lock_(g.api_mu);                             \
+  do {                                                                                   \
+    psk_status s_ = ensure_init();                                                       \
+    if (s_ != PSK_OK) return s_;                                                         \
+  } while (0)
+#define LAUNCH(kernel, grid, block, smem, ...)                                           \
+  do {                                                                                   \
+    PSK_LAUNCH(kernel, grid, block, smem, g.stream, __VA_ARGS__);                        \
+    g.launches.fetch_add(1, std::memory_order_relaxed);                                  \
+  } while (0)
+
+psk_status do_init(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    return fail(PSK_ECUDA, std::string("no CUDA device available (") +
+                               (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                               "); pskb200 has no CPU path");
+  if (device < 0 || device >= count) return fail(PSK_EINVAL, "device index out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&g.ev0));
+  CUDA_TRY(cudaEventCreate(&g.ev1));
+  CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&g.h_plan), sizeof(DPlan)));
+  CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&g.h_ctrl), 64 * sizeof(int32_t)));
+#ifndef PSK_CPU_SIM
+  cudaDeviceGetAttribute(&g.sm_count, cudaDevAttrMultiProcessorCount, device);
+  {
+    // keep freed blocks cached in the stream-ordered pool (no cudaFree round trips)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
+#endif
+  const int smem = (int)merge_eval_smem_bytes();
+  CUDA_TRY(cudaFuncSetAttribute(k_merge_eval_interp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CUDA_TRY(cudaFuncSetAttribute(k_merge_eval_interp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CUDA_TRY(cudaFuncSetAttribute(k_merge_eval_interp<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CUDA_TRY(cudaFuncSetAttribute(k_merge_eval_interp<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CUDA_TRY(cudaFuncSetAttribute(k_merge_eval_interp<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  g.device = device;
+  g.inited = true;
+  return PSK_OK;
+}
+
+psk_status ensure_init() {
+  if (g.inited) return PSK_OK;
+  std::lock_guard<std::mutex> l(g.mu);
+  if (g.inited) return PSK_OK;
+  const char* env = getenv("LOCAL_RANK");
+  return do_init(env ? atoi(env) : 0);
+}
+
+psk_status dmalloc(void** p, size_t bytes) {
+  cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 16, g.stream);
+  if (e != cudaSuccess) return fail(PSK_ENOMEM, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+  return PSK_OK;
+}
+
+int elem_size(int dtype) { return (dtype == PSK_I32 || dtype == PSK_F32) ? 4 : 1; }
+
+psk_status new_store(int dtype, int64_t capacity, psk_store_t* out) {
+  psk_store_s* s = new (std::nothrow) psk_store_s();
+  if (!s) return fail(PSK_ENOMEM, "out of host memory");
+  s->dtype = dtype;
+  s->capacity = capacity;
+  psk_status st = dmalloc(reinterpret_cast<void**>(&s->d_ends), (size_t)capacity * 4);
+  if (st == PSK_OK) st = dmalloc(reinterpret_cast<void**>(&s->d_vals), (size_t)capacity * 4);
+  if (st != PSK_OK) {
+    if (s->d_ends) cudaFreeAsync(s->d_ends, g.stream);
+    delete s;
+    return st;
+  }
+  g.live_bytes += capacity * 8;
+  *out = s;
+  return PSK_OK;
+}
+
+// ---- view descriptors ----------------------------------------------------------------
+psk_status make_dview(const psk_view& v, DView* d) {
+  memset(d, 0, sizeof(*d));
+  d->kind = v.kind;
+  if (v.kind == PSK_VIEW_AFFINE) {
+    PSK_CHECK_ARG(v.shape[0] > 0 && v.start[0] > 0 && v.stop[0] >= 0);
+    d->ndim = 1;
+    d->n = (uint32_t)v.shape[0];
+    d->c0[0] = (uint32_t)v.start[0];
+    d->c1[0] = (uint32_t)v.stop[0];
+    long long top = (long long)v.stop[0] + (long long)v.start[0] * v.shape[0];
+    PSK_CHECK_ARG(top <= 0x7fffffffLL);
+    d->m = (uint32_t)top;
+    return PSK_OK;
+  }
+  PSK_CHECK_ARG(v.kind == PSK_VIEW_GATHER || v.kind == PSK_VIEW_SCATTER);
+  PSK_CHECK_ARG(v.ndim >= 1 && v.ndim <= PSK_MAX_DIM);
+  d->ndim = v.ndim;
+  long long n = 1, m = 1;
+  for (int i = 0; i < v.ndim; ++i) {
+    // TensorSlice ctor checks, tensor.hpp:62-69, and valid(), :76-84
+    PSK_CHECK_ARG(v.shape[i] > 0);
+    PSK_CHECK_ARG(0 <= v.start[i] && v.start[i] <= v.stop[i] && v.stride[i] > 0);
+    PSK_CHECK_ARG(v.stop[i] <= v.shape[i]);
+    d->shape[i] = v.shape[i];
+    d->c0[i] = v.start[i];
+    d->c1[i] = v.stop[i];
+    d->cs[i] = v.stride[i];
+    d->cnt[i] = (uint32_t)((v.stop[i] - v.start[i] + v.stride[i] - 1) / v.stride[i]);
+    d->scale[i] = (uint32_t)n;
+    d->inner[i] = (uint32_t)m;
+    n *= v.shape[i];
+    m *= d->cnt[i];
+    PSK_CHECK_ARG(n <= 0x7fffffffLL);
+  }
+  PSK_CHECK_ARG(m > 0);  // empty selections never reach eval (array.hpp:118-120)
+  d->n = (uint32_t)n;
+  d->m = (uint32_t)m;
+  return PSK_OK;
+}
+
+// span of the view's input and output
+void dview_spans(const DView& d, int64_t* in, int64_t* out) {
+  if (d.kind == PSK_VIEW_GATHER) { *in = d.n; *out = d.m; }
+  else if (d.kind == PSK_VIEW_SCATTER) { *in = d.m; *out = d.n; }
+  else { *in = d.n; *out = d.m; }
+}
+
+int pick_K(int k) { return k <= 2 ? 2 : k <= 4 ? 4 : k <= 8 ? 8 : k <= 16 ? 16 : 32; }
+
+void launch_merge_eval(int K, int grid, DPlan* d_plan) {
+  const size_t smem = merge_eval_smem_bytes();
+  switch (K) {
+    case 2: LAUNCH(k_merge_eval_interp<2>, grid, kTileThreads, smem, d_plan); break;
+    case 4: LAUNCH(k_merge_eval_interp<4>, grid, kTileThreads, smem, d_plan); break;
+    case 8: LAUNCH(k_merge_eval_interp<8>, grid, kTileThreads, smem, d_plan); break;
+    case 16: LAUNCH(k_merge_eval_interp<16>, grid, kTileThreads, smem, d_plan); break;
+    default: LAUNCH(k_merge_eval_interp<32>, grid, kTileThreads, smem, d_plan); break;
+  }
+}
+
+psk_status validate_program(int k, int nprog, const psk_node* prog) {
+  PSK_CHECK_ARG(nprog >= 1 && nprog <= PSK_MAX_PROGRAM);
+  int depth = 0;
+  for (int i = 0; i < nprog; ++i) {
+    const int op = prog[i].op;
+    PSK_CHECK_ARG(op_known(op));
+    const int ar = op_arity(op);
+    if (op == PSK_OP_SRC) PSK_CHECK_ARG(prog[i].arg < (uint32_t)k);
+    PSK_CHECK_ARG(depth >= ar);
+    depth += 1 - ar;
+    PSK_CHECK_ARG(depth <= kMaxStack);  // lang.hpp:753 stack capacity check
+  }
+  PSK_CHECK_ARG(depth == 1);
+  return PSK_OK;
+}
+
+}  // namespace
+
+namespace {
+// checks 0 < ends[0] < ends[1] < ... on device; flag[0] |= 1 when violated
+__global__ void k_validate_runs(const int32_t* ends, int32_t n, int32_t* flag) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    int32_t prev = i ? ends[i - 1] : 0;
+    if (ends[i] <= prev) atomicOr(flag, 1);
+  }
+}
+
+__global__ void k_fill_one(int32_t* ends, uint32_t* vals, int32_t span, uint32_t bits) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    ends[0] = span;
+    vals[0] = bits;
+  }
+}
+
+// widen 1-byte host values (bool / char) to payloads
+__global__ void k_widen(const uint8_t* in, int32_t n, int is_bool, uint32_t* out) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = is_bool ? (in[i] ? 1u : 0u) : (uint32_t)(int32_t)(int8_t)in[i];
+}
+__global__ void k_narrow(const uint32_t* in, int32_t n, uint8_t* out) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint8_t)in[i];
+}
+
+psk_status finish_runs_store(psk_store_s* s, int64_t nruns) {
+  // validate on device, fetch span (= last end)
+  int32_t* d_flag = nullptr;
+  psk_status st = dmalloc(reinterpret_cast<void**>(&d_flag), 8);
+  if (st != PSK_OK) return st;
+  CUDA_TRY(cudaMemsetAsync(d_flag, 0, 8, g.stream));
+  LAUNCH(k_validate_runs, (unsigned)((nruns + 255) / 256), 256, 0, s->d_ends, (int32_t)nruns, d_flag);
+  CUDA_TRY(cudaMemcpyAsync(g.h_ctrl, d_flag, 4, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(g.h_ctrl + 1, s->d_ends + (nruns - 1), 4, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaFreeAsync(d_flag, g.stream));
+  if (g.h_ctrl[0] != 0) return fail(PSK_EINVAL, "run ends must be positive and strictly increasing");
+  s->nruns = nruns;
+  s->span = g.h_ctrl[1];
+  return PSK_OK;
+}
+}  // namespace
+
+namespace {
+template <int DT>
+psk_status encode_device(const void* d_dense, int64_t n, psk_store_t* out) {
+  const int32_t nb = (int32_t)((n + kConvChunk - 1) / kConvChunk);
+  int32_t* d_counts = nullptr;
+  psk_status st = dmalloc(reinterpret_cast<void**>(&d_counts), (size_t)(nb + 1) * 4);
+  if (st != PSK_OK) return st;
+  LAUNCH(k_encode_count<DT>, nb, kConvThreads, 0, d_dense, (long long)n, d_counts);
+  LAUNCH(k_scan_counts, 1, 1024, 0, d_counts, nb, d_counts + nb);
+  CUDA_TRY(cudaMemcpyAsync(g.h_ctrl, d_counts + nb, 4, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  const int64_t nruns = g.h_ctrl[0];
+  PSK_CHECK_STATE(nruns > 0);
+  psk_store_t s;
+  st = new_store(DT, nruns, &s);
+  if (st != PSK_OK) {
+    cudaFreeAsync(d_counts, g.stream);
+    return st;
+  }
+  LAUNCH(k_encode_write<DT>, nb, kConvThreads, 0, d_dense, (long long)n, d_counts, s->d_ends, s->d_vals);
+  CUDA_TRY(cudaFreeAsync(d_counts, g.stream));
+  s->nruns = nruns;
+  s->span = (int32_t)n;
+  *out = s;
+  return PSK_OK;
+}
+}  // namespace
+
+// ========================================================================================
+extern "C" {
+
+const char* psk_last_error(void) { return g_err.c_str(); }
+const char* psk_version(void) { return "pskb200 0.1 (sm_100a)"; }
+int32_t psk_is_simulator(void) {
+#ifdef PSK_CPU_SIM
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+psk_status psk_init(int32_t device) {
+  std::lock_guard<std::mutex> l(g.mu);
+  if (g.inited) {
+    if (device == g.device) return PSK_OK;
+    return fail(PSK_ESTATE, "pskb200 already bound to another device in this process");
+  }
+  return do_init(device);
+}
+
+psk_status psk_device_count(int32_t* count) {
+  PSK_CHECK_ARG(count != nullptr);
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  *count = (e == cudaSuccess) ? c : 0;
+  return PSK_OK;
+}
+
+psk_status psk_synchronize(void) {
+  NEED_INIT();
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  return PSK_OK;
+}
+
+psk_status psk_get_stream(void** stream) {
+  NEED_INIT();
+  PSK_CHECK_ARG(stream != nullptr);
+  *stream = (void*)g.stream;
+  return PSK_OK;
+}
+
+psk_status psk_timer_start(void) {
+  NEED_INIT();
+  CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
+  return PSK_OK;
+}
+
+psk_status psk_timer_stop(float* elapsed_ms) {
+  NEED_INIT();
+  PSK_CHECK_ARG(elapsed_ms != nullptr);
+  CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
+  CUDA_TRY(cudaEventSynchronize(g.ev1));
+  CUDA_TRY(cudaEventElapsedTime(elapsed_ms, g.ev0, g.ev1));
+  return PSK_OK;
+}
+
+int64_t psk_launch_count(int32_t reset) {
+  int64_t v = g.launches.load();
+  if (reset) g.launches.store(0);
+  return v;
+}
+
+int64_t psk_live_bytes(void) { return g.live_bytes.load(); }
+
+// ---- stores ----------------------------------------------------------------------------
+
+psk_status psk_store_from_runs(psk_dtype dtype, int64_t nruns, const int32_t* ends, const void* vals,
+                               psk_store_t* out) {
+  NEED_INIT();
+  PSK_CHECK_ARG(out != nullptr && ends != nullptr && vals != nullptr);
+  PSK_CHECK_ARG(dtype >= PSK_I32 && dtype <= PSK_CHAR);
+  PSK_CHECK_ARG(nruns > 0 && nruns < 0x7fffffffLL);  // core.hpp:33 (n > 0)
+  psk_store_t s;
+  psk_status st = new_store(dtype, nruns, &s);
+  if (st != PSK_OK) return st;
+  cudaError_t e = cudaMemcpyAsync(s->d_ends, ends, (size_t)nruns * 4, cudaMemcpyHostToDevice, g.stream);
+  if (e == cudaSuccess) {
+    if (elem_size(dtype) == 4) {
+      e = cudaMemcpyAsync(s->d_vals, vals, (size_t)nruns * 4, cudaMemcpyHostToDevice, g.stream);
+    } else {
+      uint8_t* tmp = nullptr;
+      st = dmalloc(reinterpret_cast<void**>(&tmp), (size_t)nruns);
+      if (st == PSK_OK) {
+        e = cudaMemcpyAsync(tmp, vals, (size_t)nruns, cudaMemcpyHostToDevice, g.stream);
+        LAUNCH(k_widen, (unsigned)((nruns + 255) / 256), 256, 0, tmp, (int32_t)nruns, dtype == PSK_BOOL ? 1 : 0,
+               s->d_vals);
+        cudaFreeAsync(tmp, g.stream);
+      }
+    }
+  }
+  if (e != cudaSuccess) st = fail(PSK_ECUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
+  if (st == PSK_OK) st = finish_runs_store(s, nruns);
+  if (st != PSK_OK) {
+    psk_store_release(s);
+    return st;
+  }
+  *out = s;
+  return PSK_OK;
+}
+
+psk_status psk_store_from_device_runs(psk_dtype dtype, int64_t nruns, const int32_t* d_ends,
+                                      const uint32_t* d_vals, psk_store_t* out) {
+  NEED_INIT();
+  PSK_CHECK_ARG(out != nullptr && d_ends != nullptr && d_vals != nullptr);
+  PSK_CHECK_ARG(dtype >= PSK_I32 && dtype <= PSK_CHAR);
+  PSK_CHECK_ARG(nruns > 0 && nruns < 0x7fffffffLL);
+  psk_store_t s;
+  psk_status st = new_store(dtype, nruns, &s);
+  if (st != PSK_OK) return st;
+  cudaError_t e = cudaMemcpyAsync(s->d_ends, d_ends, (size_t)nruns * 4, cudaMemcpyDeviceToDevice, g.stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(s->d_vals, d_vals, (size_t)nruns * 4, cudaMemcpyDeviceToDevice, g.stream);
+  if (e != cudaSuccess) st = fail(PSK_ECUDA, std::string("D2D copy: ") + cudaGetErrorString(e));
+  if (st == PSK_OK) st = finish_runs_store(s, nruns);
+  if (st != PSK_OK) {
+    psk_store_release(s);
+    return st;
+  }
+  *out = s;
+  return PSK_OK;
+}
+
+psk_status psk_store_fill(psk_dtype dtype, int32_t span, uint32_t fill_bits, psk_store_t* out) {
+  NEED_INIT();
+  PSK_CHECK_ARG(out != nullptr);
+  PSK_CHECK_ARG(dtype >= PSK_I32 && dtype <= PSK_CHAR);
+  PSK_CHECK_ARG(span > 0);  // core.hpp:106
+  psk_store_t s;
+  psk_status st = new_store(dtype, 1, &s);
+  if (st != PSK_OK) return st;
+  LAUNCH(k_fill_one, 1, 32, 0, s->d_ends, s->d_vals, span, fill_bits);
+  s->nruns = 1;
+  s->span = span;
+  *out = s;
+  return PSK_OK;
+}
+
+
+psk_status psk_store_from_dense_device(psk_dtype dtype, int64_t n, const void* d_dense, psk_store_t* out) {
+  NEED_INIT();
+  PSK_CHECK_ARG(out != nullptr && d_dense != nullptr);
+  PSK_CHECK_ARG(n > 0 && n <= 0x7fffffffLL);  // conv.hpp:17 (size > 0)
+  switch (dtype) {
+    case PSK_I32: return encode_device<PSK_I32>(d_dense, n, out);
+    case PSK_F32: return encode_device<PSK_F32>(d_dense, n, out);
+    case PSK_BOOL: return encode_device<PSK_BOOL>(d_dense, n, out);
+    case PSK_CHAR: return encode_device<PSK_CHAR>(d_dense, n, out);
+    default: return fail(PSK_EINVAL, "bad dtype");
+  }
+}
+
+psk_status psk_store_from_dense(psk_dtype dtype, int64_t n, const void* dense, psk_store_t* out) {
+  NEED_INIT();
+  PSK_CHECK_ARG(out != nullptr && dense != nullptr);
+  PSK_CHECK_ARG(dtype >= PSK_I32 && dtype <= PSK_CHAR);
+  PSK_CHECK_ARG(n > 0 && n <= 0x7fffffffLL);
+  void* d = nullptr;
+  const size_t bytes = (size_t)n * elem_size(dtype);
+  psk_status st = dmalloc(&d, bytes);
+  if (st != PSK_OK) return st;
+  cudaError_t e = cudaMemcpyAsync(d, dense, bytes, cudaMemcpyHostToDevice, g.stream);
+  if (e != cudaSuccess) {
+    cudaFreeAsync(d, g.stream);
+    return fail(PSK_ECUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
+  }
+  st = psk_store_from_dense_device(dtype, n, d, out);
+  cudaFreeAsync(d, g.stream);
+  return st;
+}
+
+psk_status psk_store_to_dense_device(psk_store_t s, void* d_out) {
+  NEED_INIT();
+  PSK_CHECK_ARG(s != nullptr && d_out != nullptr);
+  const long long n = s->span;
+  const unsigned nb = (unsigned)((n + kConvChunk - 1) / kConvChunk);
+  switch (s->dtype) {
+    case PSK_I32: LAUNCH(k_expand<PSK_I32>, nb, kConvThreads, 0, s->d_ends, s->d_vals, (int32_t)s->nruns, n, d_out); break;
+    case PSK_F32: LAUNCH(k_expand<PSK_F32>, nb, kConvThreads, 0, s->d_ends, s->d_vals, (int32_t)s->nruns, n, d_out); break;
+    case PSK_BOOL: LAUNCH(k_expand<PSK_BOOL>, nb, kConvThreads, 0, s->d_ends, s->d_vals, (int32_t)s->nruns, n, d_out); break;
+    default: LAUNCH(k_expand<PSK_CHAR>, nb, kConvThreads, 0, s->d_ends, s->d_vals, (int32_t)s->nruns, n, d_out); break;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return PSK_OK;
+}
+
+psk_status psk_store_to_dense(psk_store_t s, void* out_host) {
+  NEED_INIT();
+  PSK_CHECK_ARG(s != nullptr && out_host != nullptr);
+  void* d = nullptr;
+  const size_t bytes = (size_t)s->span * elem_size(s->dtype);
+  psk_status st = dmalloc(&d, bytes);
+  if (st != PSK_OK) return st;
+  st = psk_store_to_dense_device(s, d);
+  if (st == PSK_OK) {
+    cudaError_t e = cudaMemcpyAsync(out_host, d, bytes, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) st = fail(PSK_ECUDA, std::string("D2H copy: ") + cudaGetErrorString(e));
+  }
+  cudaFreeAsync(d, g.stream);
+  return st;
+}
+
+psk_status psk_store_runs(psk_store_t s, int32_t* ends, void* vals) {
+  NEED_INIT();
+  PSK_CHECK_ARG(s != nullptr && ends != nullptr && vals != nullptr);
+  const size_t n = (size_t)s->nruns;
+  CUDA_TRY(cudaMemcpyAsync(ends, s->d_ends, n * 4, cudaMemcpyDeviceToHost, g.stream));
+  if (elem_size(s->dtype) == 4) {
+    CUDA_TRY(cudaMemcpyAsync(vals, s->d_vals, n * 4, cudaMemcpyDeviceToHost, g.stream));
+  } else {
+    uint8_t* tmp = nullptr;
+    psk_status st = dmalloc(reinterpret_cast<void**>(&tmp), n);
+    if (st != PSK_OK) return st;
+    LAUNCH(k_narrow, (unsigned)((n + 255) / 256), 256, 0, s->d_vals, (int32_t)n, tmp);
+    CUDA_TRY(cudaMemcpyAsync(vals, tmp, n, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaFreeAsync(tmp, g.stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  return PSK_OK;
+}
+
+int64_t psk_store_nruns(psk_store_t s) { return s ? s->nruns : 0; }
+int32_t psk_store_span(psk_store_t s) { return s ? s->span : 0; }
+int32_t psk_store_dtype(psk_store_t s) { return s ? s->dtype : -1; }
+
+psk_status psk_store_device_ptrs(psk_store_t s, const int32_t** d_ends, const uint32_t** d_vals) {
+  PSK_CHECK_ARG(s != nullptr && d_ends != nullptr && d_vals != nullptr);
+  *d_ends = s->d_ends;
+  *d_vals = s->d_vals;
+  return PSK_OK;
+}
+
+psk_status psk_store_first_value(psk_store_t s, uint32_t* bits) {
+  NEED_INIT();
+  PSK_CHECK_ARG(s != nullptr && bits != nullptr);
+  CUDA_TRY(cudaMemcpyAsync(g.h_ctrl, s->d_vals, 4, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  *bits = (uint32_t)g.h_ctrl[0];
+  return PSK_OK;
+}
+
+psk_status psk_store_boundary(psk_store_t s, uint32_t* first_bits, uint32_t* last_bits, int64_t* nruns) {
+  NEED_INIT();
+  PSK_CHECK_ARG(s != nullptr && first_bits != nullptr && last_bits != nullptr && nruns != nullptr);
+  CUDA_TRY(cudaMemcpyAsync(g.h_ctrl, s->d_vals, 4, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(g.h_ctrl + 1, s->d_vals + (s->nruns - 1), 4, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  *first_bits = (uint32_t)g.h_ctrl[0];
+  *last_bits = (uint32_t)g.h_ctrl[1];
+  *nruns = s->nruns;
+  return PSK_OK;
+}
+
+void psk_store_retain(psk_store_t s) {
+  if (s) s->ref.fetch_add(1);
+}
+
+void psk_store_release(psk_store_t s) {
+  if (!s) return;
+  if (s->ref.fetch_sub(1) == 1) {
+    if (s->d_ends) cudaFreeAsync(s->d_ends, g.stream);
+    if (s->d_vals) cudaFreeAsync(s->d_vals, g.stream);
+    g.live_bytes -= s->capacity * 8;
+    delete s;
+  }
+}
+
+// ---- views -----------------------------------------------------------------------------
+psk_status psk_view_span(int32_t span_in, int32_t nviews, const psk_view* views, int32_t* span_out) {
+  PSK_CHECK_ARG(span_out != nullptr && nviews >= 0 && nviews <= PSK_MAX_VIEWS);
+  int64_t cur = span_in;
+  for (int i = 0; i < nviews; ++i) {
+    DView d;
+    psk_status st = make_dview(views[i], &d);
+    if (st != PSK_OK) return st;
+    int64_t in, out;
+    dview_spans(d, &in, &out);
+    // Array::get / Tensor::get argument checks (array.hpp:117, tensor.hpp:272, :293)
+    if (in != cur) return fail(PSK_EINVAL, "view does not match the span of its input");
+    cur = out;
+  }
+  *span_out = (int32_t)cur;
+  return PSK_OK;
+}
+
+// ---- the hot path ----------------------------------------------------------------------
+psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const psk_node* prog,
+                    psk_dtype out_dtype, psk_eq eq, psk_store_t* out) {
+  NEED_INIT();
+  PSK_CHECK_ARG(out != nullptr && sources != nullptr && prog != nullptr);
+  PSK_CHECK_ARG(k >= 1 && k <= PSK_MAX_SOURCES);  // lang.hpp:789-857
+  PSK_CHECK_ARG(out_dtype >= PSK_I32 && out_dtype <= PSK_CHAR);
+  psk_status st = validate_program(k, nprog, prog);
+  if (st != PSK_OK) return st;
+
+  DPlan& hp = *g.h_plan;
+  hp.k = k;
+  hp.eq = (eq == PSK_EQ_TYPED && out_dtype == PSK_F32) ? 1 : 0;
+  hp.nprog = nprog;
+  memcpy(hp.prog, prog, sizeof(psk_node) * (size_t)nprog);
+
+  int64_t span = -1;
+  int64_t total_runs = 0;
+  bool any_views = false;
+  for (int i = 0; i < k; ++i) {
+    const psk_source& s = sources[i];
+    PSK_CHECK_ARG(s.store != nullptr);
+    PSK_CHECK_ARG(s.nviews >= 0 && s.nviews <= PSK_MAX_VIEWS);
+    DSource& d = hp.src[i];
+    d.ends = s.store->d_ends;
+    d.vals = s.store->d_vals;
+    d.nruns = (int32_t)s.store->nruns;
+    d.nviews = s.nviews;
+    int64_t cur = s.store->span;
+    for (int v = 0; v < s.nviews; ++v) {
+      st = make_dview(s.views[v], &d.v[v]);
+      if (st != PSK_OK) return st;
+      int64_t in, o;
+      dview_spans(d.v[v], &in, &o);
+      if (in != cur) return fail(PSK_EINVAL, "view does not match the span of its input");
+      cur = o;
+    }
+    if (s.nviews) any_views = true;
+    // every source of a pool must share the output span (eval.hpp:400-403, lang.hpp:198)
+    if (span < 0) span = cur;
+    else if (span != cur) return fail(PSK_EINVAL, "sources have different spans");
+    total_runs += d.nruns;
+  }
+  PSK_CHECK_ARG(span > 0);  // eval.hpp:611
+  PSK_CHECK_ARG(total_runs < 0x7ffffff0LL);
+  hp.span = (int32_t)span;
+  hp.any_views = any_views ? 1 : 0;
+
+  // ---- partition parameters: S * (m + 2k) <= kTileCap bounds the runs of one tile --------
+  int S = k <= 4 ? 256 : k <= 8 ? 128 : k <= 16 ? 64 : 32;
+  while (S > 32 && total_runs / S < 2048) S >>= 1;
+  int64_t max_samples = 0;
+  for (int i = 0; i < k; ++i) max_samples += (hp.src[i].nruns + S - 1) / S;
+  const int m_max = kTileCap / S - 2 * k;
+  int m = (int)(max_samples / (2 * (int64_t)g.sm_count));
+  if (m > m_max) m = m_max;
+  if (m < 1) m = 1;
+  const int64_t max_tiles = (max_samples + m - 1) / m + 1;
+  hp.S = S;
+  hp.m = m;
+  hp.max_tiles = (int32_t)max_tiles;
+  if (!any_views) {
+    int32_t off = 0;
+    for (int i = 0; i < k; ++i) {
+      DSource& d = hp.src[i];
+      d.a = 0;
+      d.e = d.nruns;
+      d.ns = (d.nruns + S - 1) / S;
+      d.samp_off = off;
+      off += d.ns;
+    }
+    hp.total_samples = off;
+    hp.n_tiles = (off + m - 1) / m;
+  } else {
+    hp.total_samples = 0;
+    hp.n_tiles = 0;
+  }
+
+  // ---- scratch: [tile_state | ctrl | merged | bounds | tile_hi | plan] --------------------
+  size_t o_state = 0;
+  size_t o_ctrl = o_state + (size_t)max_tiles * 8;
+  size_t o_merged = o_ctrl + CTRL_WORDS * 4;
+  size_t o_bounds = o_merged + (size_t)max_samples * 4;
+  size_t o_hi = o_bounds + (size_t)(max_tiles + 1) * k * 4;
+  size_t o_plan = (o_hi + (size_t)max_tiles * 4 + 15) & ~(size_t)15;
+  const size_t plan_bytes = offsetof(DPlan, src) + sizeof(DSource) * (size_t)k;
+  size_t scratch_bytes = o_plan + sizeof(DPlan);
+  unsigned char* scratch = nullptr;
+  st = dmalloc(reinterpret_cast<void**>(&scratch), scratch_bytes);
+  if (st != PSK_OK) return st;
+  psk_store_t res = nullptr;
+  st = new_store(out_dtype, total_runs, &res);
+  if (st != PSK_OK) {
+    cudaFreeAsync(scratch, g.stream);
+    return st;
+  }
+  hp.tile_state = reinterpret_cast<unsigned long long*>(scratch + o_state);
+  hp.ctrl = reinterpret_cast<int32_t*>(scratch + o_ctrl);
+  hp.merged = reinterpret_cast<int32_t*>(scratch + o_merged);
+  hp.bounds = reinterpret_cast<int32_t*>(scratch + o_bounds);
+  hp.tile_hi = reinterpret_cast<int32_t*>(scratch + o_hi);
+  hp.out_ends = res->d_ends;
+  hp.out_vals = res->d_vals;
+  hp.out_capacity = (int32_t)total_runs;
+  DPlan* d_plan = reinterpret_cast<DPlan*>(scratch + o_plan);
+
+  cudaError_t e = cudaMemsetAsync(scratch, 0, o_merged, g.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_plan, &hp, plan_bytes, cudaMemcpyHostToDevice, g.stream);
+  if (e == cudaSuccess) {
+    if (any_views) LAUNCH(k_prepare, 1, 32, 0, d_plan);
+    LAUNCH(k_sample_rank, (unsigned)((max_samples + 255) / 256), 256, 0, d_plan);
+    LAUNCH(k_tile_bounds, (unsigned)(((max_tiles + 1) * k + 255) / 256), 256, 0, d_plan);
+    int64_t grid = 2 * (int64_t)g.sm_count;
+    if (grid > max_tiles) grid = max_tiles;
+    launch_merge_eval(pick_K(k), (int)grid, d_plan);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(g.h_ctrl, hp.ctrl, CTRL_WORDS * 4, cudaMemcpyDeviceToHost, g.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+  cudaFreeAsync(scratch, g.stream);
+  if (e != cudaSuccess) {
+    psk_store_release(res);
+    return fail(PSK_ECUDA, std::string("psk_eval: ") + cudaGetErrorString(e));
+  }
+  if (g.h_ctrl[CTRL_ERROR] != 0) {
+    psk_store_release(res);
+    return fail(PSK_ESTATE, "psk_eval: tile capacity exceeded (internal partition bound violated)");
+  }
+  res->nruns = g.h_ctrl[CTRL_COUNT];
+  res->span = (int32_t)span;
+  if (res->nruns <= 0) {
+    psk_store_release(res);
+    return fail(PSK_ESTATE, "psk_eval: produced no runs");
+  }
+  *out = res;
+  return PSK_OK;
+}
+
+// ---- masks -----------------------------------------------------------------------------
+psk_status psk_mask_nd(int32_t ndim, const int32_t* shape, const int32_t* start, const int32_t* stop,
+                       const int32_t* stride, psk_store_t* out) {
+  NEED_INIT();
+  PSK_CHECK_ARG(out != nullptr && shape && start && stop && stride);
+  PSK_CHECK_ARG(ndim >= 1 && ndim <= PSK_MAX_DIM);
+  psk_view v;
+  memset(&v, 0, sizeof(v));
+  v.kind = PSK_VIEW_GATHER;
+  v.ndim = ndim;
+  for (int i = 0; i < ndim; ++i) {
+    v.shape[i] = shape[i];
+    v.start[i] = start[i];
+    v.stop[i] = stop[i];
+    v.stride[i] = stride[i];
+  }
+  DView d;
+  psk_status st = make_dview(v, &d);
+  if (st != PSK_OK) return st;
+  const uint32_t seg_len = d.cs[0] == 1 ? d.cnt[0] : 1;
+  const int64_t nseg = d.m / seg_len;
+  const int64_t nraw = 2 * nseg + 1;
+  PSK_CHECK_ARG(nraw < 0x7fffffffLL);
+  // raw (non-canonical) run list, then canonicalise with the eval kernel: an AFFINE
+  // identity view routes it through the path that drops zero-length runs
+  psk_store_t raw;
+  st = new_store(PSK_BOOL, nraw, &raw);
+  if (st != PSK_OK) return st;
+  LAUNCH(k_mask_segments, (unsigned)((nseg + 255) / 256), 256, 0, d, seg_len, (int32_t)nseg, raw->d_ends, raw->d_vals);
+  raw->nruns = nraw;
+  raw->span = (int32_t)d.n;
+  psk_source src;
+  memset(&src, 0, sizeof(src));
+  src.store = raw;
+  src.nviews = 1;
+  src.views[0].kind = PSK_VIEW_AFFINE;
+  src.views[0].ndim = 1;
+  src.views[0].shape[0] = (int32_t)d.n;
+  src.views[0].start[0] = 1;
+  src.views[0].stop[0] = 0;
+  psk_node prog{PSK_OP_SRC, 0};
+  st = psk_eval(1, &src, 1, &prog, PSK_BOOL, PSK_EQ_BITWISE, out);
+  psk_store_release(raw);
+  return st;
+}
+
+// ---- reductions ------------------------------------------------------------------------
+psk_status psk_reduce(psk_store_t s, psk_reduce_op op, uint64_t* result_bits) {
+  NEED_INIT();
+  PSK_CHECK_ARG(s != nullptr && result_bits != nullptr);
+  PSK_CHECK_ARG(op >= PSK_RED_SUM && op <= PSK_RED_PROD);
+  const bool is_f = s->dtype == PSK_F32;
+  int nblocks = (int)((s->nruns + kRedThreads - 1) / kRedThreads);
+  if (nblocks > kRedBlocks) nblocks = kRedBlocks;
+  RedAcc* d_part = nullptr;
+  psk_status st = dmalloc(reinterpret_cast<void**>(&d_part), sizeof(RedAcc) * (size_t)(nblocks + 1));
+  if (st != PSK_OK) return st;
+  if (is_f) {
+    LAUNCH(k_reduce_partial<true>, nblocks, kRedThreads, 0, s->d_ends, s->d_vals, (int32_t)s->nruns, (int)op, d_part);
+    LAUNCH(k_reduce_final<true>, 1, kRedThreads, 0, d_part, nblocks, (int)op, d_part + nblocks);
+  } else {
+    LAUNCH(k_reduce_partial<false>, nblocks, kRedThreads, 0, s->d_ends, s->d_vals, (int32_t)s->nruns, (int)op, d_part);
+    LAUNCH(k_reduce_final<false>, 1, kRedThreads, 0, d_part, nblocks, (int)op, d_part + nblocks);
+  }
+  RedAcc* h = reinterpret_cast<RedAcc*>(g.h_ctrl);
+  CUDA_TRY(cudaMemcpyAsync(h, d_part + nblocks, sizeof(RedAcc), cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaFreeAsync(d_part, g.stream));
+  if (op == PSK_RED_MAX) *result_bits = h->mx;
+  else if (op == PSK_RED_MIN) *result_bits = h->mn;
+  else if (is_f) memcpy(result_bits, &h->fsum, 8);
+  else *result_bits = h->isum;
+  return PSK_OK;
+}
+
+psk_status psk_store_slice(psk_store_t s, int32_t start, int32_t stop, psk_store_t* out) {
+  NEED_INIT();
+  PSK_CHECK_ARG(s != nullptr && out != nullptr);
+  PSK_CHECK_ARG(0 <= start && start < stop && stop <= s->span);
+  psk_source src;
+  memset(&src, 0, sizeof(src));
+  src.store = s;
+  src.nviews = 1;
+  src.views[0].kind = PSK_VIEW_GATHER;
+  src.views[0].ndim = 1;
+  src.views[0].shape[0] = s->span;
+  src.views[0].start[0] = start;
+  src.views[0].stop[0] = stop;
+  src.views[0].stride[0] = 1;
+  psk_node prog{PSK_OP_SRC, 0};
+  return psk_eval(1, &src, 1, &prog, (psk_dtype)s->dtype, PSK_EQ_BITWISE, out);
+}
+
+}  // extern "C"
