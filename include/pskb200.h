@@ -145,6 +145,9 @@ PSK_API psk_status psk_device_count(int32_t* count);
 PSK_API psk_status psk_synchronize(void);
 /* Raw cudaStream_t of the library stream (for event timing / interop). */
 PSK_API psk_status psk_get_stream(void** stream);
+/* Make the library issue all further work on a caller-owned cudaStream_t (e.g. torch's
+ * current stream, so NCCL collectives and library kernels share one timeline). */
+PSK_API psk_status psk_set_stream(void* stream);
 /* Device-side timer on the library stream (CUDA events). */
 PSK_API psk_status psk_timer_start(void);
 PSK_API psk_status psk_timer_stop(float* elapsed_ms);
@@ -152,6 +155,12 @@ PSK_API psk_status psk_timer_stop(float* elapsed_ms);
 PSK_API int64_t psk_launch_count(int32_t reset);
 /* Bytes currently held by live stores. */
 PSK_API int64_t psk_live_bytes(void);
+/* Measurement aid for bench.py's roofline line: when enabled, psk_eval brackets its
+ * dominant kernel (k_merge_eval) with CUDA events on the library stream and accumulates
+ * the elapsed time, the number of evaluations and the runs read / written. */
+PSK_API psk_status psk_profile(int32_t enable);
+PSK_API psk_status psk_profile_read(double* merge_eval_ms, int64_t* evals, int64_t* runs_in,
+                                    int64_t* runs_out);
 
 /* ---- stores: core::Store (detail/core.hpp:12-62) ----------------------------------- */
 /* From host run arrays (core::Store ctor; validated: n>0, ends strictly increasing). */

@@ -103,8 +103,8 @@ def make_view(kind, shape, comps=None, scale=None, offset=None) -> View:
 
 _SYMBOLS = [
     "psk_last_error", "psk_version", "psk_is_simulator", "psk_init", "psk_device_count",
-    "psk_synchronize", "psk_get_stream", "psk_timer_start", "psk_timer_stop", "psk_launch_count",
-    "psk_live_bytes", "psk_store_from_runs", "psk_store_from_device_runs", "psk_store_fill",
+    "psk_synchronize", "psk_get_stream", "psk_set_stream", "psk_timer_start", "psk_timer_stop", "psk_launch_count",
+    "psk_live_bytes", "psk_profile", "psk_profile_read", "psk_store_from_runs", "psk_store_from_device_runs", "psk_store_fill",
     "psk_store_from_dense", "psk_store_from_dense_device", "psk_store_to_dense",
     "psk_store_to_dense_device", "psk_store_runs", "psk_store_nruns", "psk_store_span",
     "psk_store_dtype", "psk_store_device_ptrs", "psk_store_first_value", "psk_store_retain",
@@ -204,6 +204,7 @@ class Lib:
         c.psk_init.argtypes = [C.c_int32]
         c.psk_timer_stop.argtypes = [C.c_void_p]
         c.psk_get_stream.argtypes = [C.c_void_p]
+        c.psk_set_stream.argtypes = [C.c_void_p]
         c.psk_device_count.argtypes = [C.c_void_p]
         c.psk_launch_count.argtypes = [C.c_int32]
         self._lock = threading.Lock()
@@ -230,6 +231,9 @@ class Lib:
     def synchronize(self):
         self._chk(self.c.psk_synchronize())
 
+    def set_stream(self, cuda_stream: int):
+        self._chk(self.c.psk_set_stream(C.c_void_p(cuda_stream)))
+
     def timer_start(self):
         self._chk(self.c.psk_timer_start())
 
@@ -240,6 +244,15 @@ class Lib:
 
     def launch_count(self, reset=False) -> int:
         return self.c.psk_launch_count(1 if reset else 0)
+
+    def profile(self, enable: bool):
+        self._chk(self.c.psk_profile(1 if enable else 0))
+
+    def profile_read(self):
+        """-> (merge_eval_ms_total, evals, runs_in, runs_out) since profile(True)."""
+        ms, n, ri, ro = C.c_double(), C.c_int64(), C.c_int64(), C.c_int64()
+        self._chk(self.c.psk_profile_read(C.byref(ms), C.byref(n), C.byref(ri), C.byref(ro)))
+        return ms.value, n.value, ri.value, ro.value
 
     # -- stores -----------------------------------------------------------------------
     def store_from_runs(self, ends, vals) -> Store:

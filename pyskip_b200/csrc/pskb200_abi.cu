@@ -41,6 +41,11 @@ struct Ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t pev0 = nullptr, pev1 = nullptr;  // bracket the merge/eval kernel when profiling
+  bool profile = false;
+  double prof_ms = 0.0;
+  int64_t prof_n = 0;
+  int64_t prof_runs_in = 0, prof_runs_out = 0;
   DPlan* h_plan = nullptr;      // pinned staging copy of the plan
   int32_t* h_ctrl = nullptr;    // pinned read-back of CTRL words / small results
   std::atomic<int64_t> launches{0};
@@ -93,6 +98,8 @@ psk_status do_init(int device) {
   CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&g.ev0));
   CUDA_TRY(cudaEventCreate(&g.ev1));
+  CUDA_TRY(cudaEventCreate(&g.pev0));
+  CUDA_TRY(cudaEventCreate(&g.pev1));
   CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&g.h_plan), sizeof(DPlan)));
   CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&g.h_ctrl), 64 * sizeof(int32_t)));
 #ifndef PSK_CPU_SIM
@@ -345,6 +352,15 @@ psk_status psk_get_stream(void** stream) {
   return PSK_OK;
 }
 
+psk_status psk_set_stream(void* stream) {
+  NEED_INIT();
+  // adopt a caller-owned stream (e.g. torch's current stream) so that library work and the
+  // caller's collectives are ordered on -- and timed by events of -- one stream
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  g.stream = (cudaStream_t)stream;
+  return PSK_OK;
+}
+
 psk_status psk_timer_start(void) {
   NEED_INIT();
   CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
@@ -367,6 +383,23 @@ int64_t psk_launch_count(int32_t reset) {
 }
 
 int64_t psk_live_bytes(void) { return g.live_bytes.load(); }
+
+psk_status psk_profile(int32_t enable) {
+  g.profile = enable != 0;
+  g.prof_ms = 0.0;
+  g.prof_n = 0;
+  g.prof_runs_in = g.prof_runs_out = 0;
+  return PSK_OK;
+}
+
+psk_status psk_profile_read(double* merge_eval_ms, int64_t* evals, int64_t* runs_in, int64_t* runs_out) {
+  PSK_CHECK_ARG(merge_eval_ms && evals && runs_in && runs_out);
+  *merge_eval_ms = g.prof_ms;
+  *evals = g.prof_n;
+  *runs_in = g.prof_runs_in;
+  *runs_out = g.prof_runs_out;
+  return PSK_OK;
+}
 
 // ---- stores ----------------------------------------------------------------------------
 
@@ -703,7 +736,9 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
     LAUNCH(k_tile_bounds, (unsigned)(((max_tiles + 1) * k + 255) / 256), 256, 0, d_plan);
     int64_t grid = 2 * (int64_t)g.sm_count;
     if (grid > max_tiles) grid = max_tiles;
+    if (g.profile) cudaEventRecord(g.pev0, g.stream);
     launch_merge_eval(pick_K(k), (int)grid, d_plan);
+    if (g.profile) cudaEventRecord(g.pev1, g.stream);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(g.h_ctrl, hp.ctrl, CTRL_WORDS * 4, cudaMemcpyDeviceToHost, g.stream);
@@ -719,6 +754,15 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
   }
   res->nruns = g.h_ctrl[CTRL_COUNT];
   res->span = (int32_t)span;
+  if (g.profile) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g.pev0, g.pev1) == cudaSuccess) {
+      g.prof_ms += ms;
+      g.prof_n += 1;
+      g.prof_runs_in += total_runs;
+      g.prof_runs_out += res->nruns;
+    }
+  }
   if (res->nruns <= 0) {
     psk_store_release(res);
     return fail(PSK_ESTATE, "psk_eval: produced no runs");

@@ -1,0 +1,198 @@
+"""Parity of the C-ABI eval path (k-way merge + fused program + compaction) with the oracle.
+
+Each test runs on the CUDA library (`-m gpu`, the parity tests proper) and, at small sizes,
+on the kernel-logic simulator (CPU CI).  Integer results and run structure must be
+bit-exact; float32 programs here use only correctly rounded ops (+ - * / sqrt abs min max),
+so they are compared bit for bit as well (tolerance 0).
+"""
+import numpy as np
+import pytest
+
+from helpers import A, O, assert_runs_equal, oracle_eval, rand_runs, run_eval
+
+
+def test_eval_simple_kat(lib):
+    # tests/eval_test.cpp:14-24  "1=>4, 2=>10, 3=>18"
+    s = (np.array([1, 2, 3], np.int32), np.array([1, 2, 3], np.int32), [])
+    t = (np.array([1, 2, 3], np.int32), np.array([4, 5, 6], np.int32), [])
+    e, v = run_eval(lib, [s, t], ("mul", ("src", 0), ("src", 1)))
+    assert O.to_string(e, v) == "1=>4, 2=>10, 3=>18"
+
+
+def test_eval_select_kat(lib):
+    # tests/eval_test.cpp:26-43 (eval_mixed select): "1=>a, 2=>b, 3=>c"
+    m = O.to_store(np.array([False, True, False]))
+    s = O.to_store(np.frombuffer(b"axc", dtype=np.int8))
+    t = O.to_store(np.frombuffer(b"xbx", dtype=np.int8))
+    e, v = run_eval(lib, [m + ([],), s + ([],), t + ([],)], ("select", ("src", 0), ("src", 2), ("src", 1)))
+    assert O.to_string(e, v) == "1=>a, 2=>b, 3=>c"
+
+
+def test_eval_weave_kat(lib):
+    # tests/eval_test.cpp:45-64: two stores woven by a scaled<2> step function
+    m = O.to_store(np.array([0, 1, 0, 1, 0, 1], np.int32))
+    s = O.to_store(np.frombuffer(b"ace", dtype=np.int8))
+    t = O.to_store(np.frombuffer(b"bdf", dtype=np.int8))
+    view = [("affine", 2, 0, 3)]
+    e, v = run_eval(lib, [m + ([],), s + (view,), t + (view,)],
+                    ("select", ("cast", np.bool_, ("src", 0)), ("src", 2), ("src", 1)))
+    assert O.to_string(e, v) == "1=>a, 2=>b, 3=>c, 4=>d, 5=>e, 6=>f"
+
+
+def test_fused_zeros_single_run(lib, scale):
+    # tests/benchmarks/eval_bench.cpp:86-101: a 4-source product of zeros fuses to one run
+    n = 4096 * scale
+    ends = np.arange(1, n + 1, dtype=np.int32)
+    srcs = [(ends, np.zeros(n, np.int32), []) for _ in range(4)]
+    expr = ("mul", ("mul", ("src", 0), ("src", 1)), ("mul", ("src", 2), ("src", 3)))
+    e, v = run_eval(lib, srcs, expr)
+    assert e.tolist() == [n] and v.tolist() == [0]
+
+
+def test_interleaved_add(lib, scale):
+    # tests/benchmarks/array_bench.cpp:183-227 shape: k interleaved one-hot sources sum to "n=>1"
+    k, n = 8, 2000 * scale
+    srcs = []
+    for i in range(k):
+        dense = np.zeros(n, np.int32)
+        dense[i::k] = 1
+        srcs.append(O.to_store(dense) + ([],))
+    expr = ("src", 0)
+    for i in range(1, k):
+        expr = ("add", expr, ("src", i))
+    e, v = run_eval(lib, srcs, expr)
+    assert e.tolist() == [n] and v.tolist() == [1]
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 9, 17, 32])
+def test_random_int_kway(lib, scale, k):
+    rng = np.random.default_rng(100 + k)
+    span = 20000 * scale
+    srcs = [rand_runs(rng, span, int(rng.integers(1, 3000 * scale // max(1, k // 4)))) + ([],) for _ in range(k)]
+    expr = ("src", 0)
+    for i in range(1, k):
+        expr = ("add", expr, ("mul", ("src", i), ("const", i + 1, np.int32)))
+    assert_runs_equal(run_eval(lib, srcs, expr), oracle_eval(srcs, expr))
+
+
+def test_skewed_sources(lib, scale):
+    # a 3-run mask merged with dense stores; all runs clustered in 1% of the span
+    rng = np.random.default_rng(7)
+    span = 1_000_000 * scale
+    nr = 6000 * scale
+    cuts = np.sort(rng.choice(np.arange(span // 2, span // 2 + span // 100), size=nr - 1, replace=False))
+    a = (np.concatenate([cuts, [span]]).astype(np.int32), rng.integers(0, 9, nr).astype(np.int32), [])
+    b = (np.array([span // 3, span // 2 + 50, span], np.int32), np.array([1, 0, 1], np.int32), [])
+    c = rand_runs(rng, span, 50) + ([],)
+    expr = ("add", ("mul", ("src", 0), ("src", 1)), ("src", 2))
+    assert_runs_equal(run_eval(lib, [a, b, c], expr), oracle_eval([a, b, c], expr))
+
+
+def test_c1_shape(lib, scale):
+    # BASELINE config 1 shape: int32 a + b*c over ~10k-run operands (n scaled down on the sim)
+    rng = np.random.default_rng(1000)
+    n = 10_000_000 if scale > 1 else 200_000
+    r = 10_000 if scale > 1 else 2_000
+    srcs = [rand_runs(rng, n, r, lo=0, hi=1000) + ([],) for _ in range(3)]
+    expr = ("add", ("src", 0), ("mul", ("src", 1), ("src", 2)))
+    assert_runs_equal(run_eval(lib, srcs, expr), oracle_eval(srcs, expr))
+
+
+@pytest.mark.parametrize("eq", ["bitwise", "typed"])
+def test_c2_float_dag(lib, scale, eq):
+    # BASELINE config 2 DAG at reduced size: max(a*b + c, d) - abs(a) * 0.5f
+    rng = np.random.default_rng(2000)
+    span = 1_000_000 * scale
+    srcs = [rand_runs(rng, span, 10_000 * scale, np.float32, 0, 64) + ([],) for _ in range(4)]
+    a, b, c, d = [("src", i) for i in range(4)]
+    expr = ("sub", ("max", ("add", ("mul", a, b), c), d), ("mul", ("abs", a), ("const", 0.5, np.float32)))
+    assert_runs_equal(run_eval(lib, srcs, expr, eq), oracle_eval(srcs, expr, eq))
+
+
+def test_float_signed_zero_nan(lib):
+    # typed equality merges -0/+0 (later value wins) and never merges NaN;
+    # bitwise equality does the opposite
+    x = np.array([0, -0.0, 0, 1, np.nan, np.nan, 2, -0.0, -0.0, 0], np.float32)
+    ends = np.arange(1, 11, dtype=np.int32)
+    for eq in ("typed", "bitwise"):
+        got = run_eval(lib, [(ends, x, [])], ("mul", ("src", 0), ("const", 1.0, np.float32)), eq)
+        want = oracle_eval([(ends, x, [])], ("mul", ("src", 0), ("const", 1.0, np.float32)), eq)
+        assert_runs_equal(got, want, eq)
+    st = lib.store_from_dense(x)
+    e, v = st.runs()
+    assert e.tolist() == [3, 4, 5, 6, 7, 10]          # observed on the reference
+
+
+def test_int_op_catalogue(lib):
+    rng = np.random.default_rng(5)
+    span = 3000
+    a = rand_runs(rng, span, 300, lo=-50, hi=50) + ([],)
+    b = rand_runs(rng, span, 200, lo=1, hi=9) + ([],)
+    A_, B_ = ("src", 0), ("src", 1)
+    for name in ["add", "sub", "mul", "div", "mod", "band", "bor", "bxor", "shl", "shr", "min", "max",
+                 "coalesce", "eq", "ne", "lt", "gt", "le", "ge", "land", "lor", "pow"]:
+        expr = (name, A_, B_)
+        assert_runs_equal(run_eval(lib, [a, b], expr), oracle_eval([a, b], expr), name)
+    for name in ["neg", "abs", "bnot", "lnot"]:
+        assert_runs_equal(run_eval(lib, [a], (name, A_)), oracle_eval([a], (name, A_)), name)
+    pos = rand_runs(rng, span, 100, lo=0, hi=2000) + ([],)
+    assert_runs_equal(run_eval(lib, [pos], ("sqrt", A_)), oracle_eval([pos], ("sqrt", A_)), "sqrt")
+    small = rand_runs(rng, span, 100, lo=-3, hi=15) + ([],)
+    assert_runs_equal(run_eval(lib, [small], ("exp", A_)), oracle_eval([small], ("exp", A_)), "exp")
+    # wrap-around: INT_MAX + 1 -> INT_MIN
+    big = (np.array([span], np.int32), np.array([2 ** 31 - 1], np.int32), [])
+    e, v = run_eval(lib, [big], ("add", A_, ("const", 1, np.int32)))
+    assert v.tolist() == [-2 ** 31]
+    # -7 // 2 -> -3, -7 % 3 -> -1
+    m7 = (np.array([span], np.int32), np.array([-7], np.int32), [])
+    assert run_eval(lib, [m7], ("div", A_, ("const", 2, np.int32)))[1].tolist() == [-3]
+    assert run_eval(lib, [m7], ("mod", A_, ("const", 3, np.int32)))[1].tolist() == [-1]
+
+
+def test_float_op_catalogue(lib):
+    rng = np.random.default_rng(6)
+    span = 3000
+    a = rand_runs(rng, span, 300, np.float32, 0, 64) + ([],)
+    b = rand_runs(rng, span, 200, np.float32, 0, 16) + ([],)
+    A_, B_ = ("src", 0), ("src", 1)
+    exact = ["add", "sub", "mul", "div", "mod", "min", "max", "coalesce", "eq", "ne", "lt", "gt", "le", "ge",
+             "land", "lor"]
+    for name in exact:
+        expr = (name, A_, B_)
+        assert_runs_equal(run_eval(lib, [a, b], expr), oracle_eval([a, b], expr), name)
+    for name in ["neg", "abs", "sqrt", "lnot"]:
+        assert_runs_equal(run_eval(lib, [a], (name, A_)), oracle_eval([a], (name, A_)), name)
+    # exp / pow: libm-rounding dependent -> 1e-6 relative on values, same run structure here
+    for expr in [("exp", A_), ("pow", A_, B_)]:
+        ge, gv = run_eval(lib, [a, b], expr)
+        we, wv = oracle_eval([a, b], expr)
+        assert np.array_equal(ge, we)
+        assert np.allclose(gv, wv, rtol=1e-6, atol=0)
+    # (3 * 1.0) % 2.0 == 1.0   tests/array_test.cpp:97-108
+    one = (np.array([5], np.int32), np.array([1.0], np.float32), [])
+    e, v = run_eval(lib, [one], ("mod", ("mul", ("const", 3.0, np.float32), A_), ("const", 2.0, np.float32)))
+    assert v.tolist() == [1.0]
+
+
+def test_casts(lib):
+    rng = np.random.default_rng(8)
+    span = 2000
+    f = (np.arange(1, span + 1, dtype=np.int32), (rng.integers(-3000, 3000, span) * 0.37).astype(np.float32), [])
+    i = rand_runs(rng, span, 200, lo=-300, hi=300) + ([],)
+    for dt in (np.int32, np.bool_, np.int8, np.float32):
+        for src in (f, i):
+            expr = ("cast", dt, ("src", 0))
+            assert_runs_equal(run_eval(lib, [src], expr), oracle_eval([src], expr), f"{dt}")
+
+
+def test_arg_errors(lib):
+    st = lib.store_fill(A.I32, 10, 1)
+    st2 = lib.store_fill(A.I32, 11, 1)
+    with pytest.raises(ValueError):       # eval.hpp:400-403 span mismatch -> invalid_argument
+        lib.eval([(st, []), (st2, [])], [(A.OP_SRC, 0), (A.OP_SRC, 1), (A.OP_I["add"], 0)], A.I32)
+    with pytest.raises(ValueError):
+        lib.eval([(st, [])], [(A.OP_SRC, 0), (A.OP_I["add"], 0)], A.I32)   # stack underflow
+    with pytest.raises(ValueError):
+        lib.store_from_runs(np.array([3, 3], np.int32), np.array([1, 2], np.int32))
+    with pytest.raises(ValueError):
+        lib.store_fill(A.I32, 0, 1)       # core.hpp:106 span > 0
