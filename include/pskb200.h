@@ -34,8 +34,17 @@
 #ifndef PSKB200_H_
 #define PSKB200_H_
 
+#ifdef __CUDACC_RTC__ /* run-time compilation of the kernel templates: no system headers */
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#else
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -56,7 +65,7 @@ enum {
   PSK_ENOMEM = 4
 };
 
-/* Element types bound by the reference (src/cpp_ext/binds/*_binds.cpp:3-5). */
+/* Element types bound by the reference (src/cpp_ext/binds/{int,float,bool,char}_binds.cpp:3-5). */
 typedef enum { PSK_I32 = 0, PSK_F32 = 1, PSK_BOOL = 2, PSK_CHAR = 3 } psk_dtype;
 
 /* Equality used by run compaction:
@@ -133,6 +142,7 @@ typedef struct {
 
 typedef enum { PSK_RED_SUM = 0, PSK_RED_MAX = 1, PSK_RED_MIN = 2, PSK_RED_PROD = 3 } psk_reduce_op;
 
+#ifndef __CUDACC_RTC__ /* the entry points are host functions */
 /* ---- library / device ------------------------------------------------------------- */
 PSK_API const char* psk_last_error(void);
 PSK_API const char* psk_version(void);
@@ -155,6 +165,16 @@ PSK_API psk_status psk_timer_stop(float* elapsed_ms);
 PSK_API int64_t psk_launch_count(int32_t reset);
 /* Bytes currently held by live stores. */
 PSK_API int64_t psk_live_bytes(void);
+/* Evaluations whose sources hold at least `min_total_runs` runs use a kernel specialised for
+ * their program at run time (NVRTC; the generic interpreter kernel otherwise or when NVRTC
+ * is unavailable).  Negative: never.  Default 2^18. */
+PSK_API psk_status psk_set_jit_threshold(int64_t min_total_runs);
+/* NVRTC stage of the specialisation only (needs no GPU): 0 when the kernel specialised for
+ * `prog` over k sources compiles to an sm_100a cubin; the compiler log goes to `log`. */
+PSK_API int32_t psk_jit_compile_check(int32_t k, int32_t nprog, const psk_node* prog, char* log,
+                                      int32_t loglen);
+/* How many psk_eval calls ran on a specialised kernel. */
+PSK_API int64_t psk_jit_launch_count(void);
 /* Measurement aid for bench.py's roofline line: when enabled, psk_eval brackets its
  * dominant kernel (k_merge_eval) with CUDA events on the library stream and accumulates
  * the elapsed time, the number of evaluations and the runs read / written. */
@@ -223,6 +243,7 @@ PSK_API psk_status psk_store_boundary(psk_store_t s, uint32_t* first_bits, uint3
                                       int64_t* nruns);
 /* Sub-range [start, stop) of a store re-based to 0 (SimpleSource::split, eval.hpp:281-287). */
 PSK_API psk_status psk_store_slice(psk_store_t s, int32_t start, int32_t stop, psk_store_t* out);
+#endif /* !__CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

@@ -104,7 +104,7 @@ def make_view(kind, shape, comps=None, scale=None, offset=None) -> View:
 _SYMBOLS = [
     "psk_last_error", "psk_version", "psk_is_simulator", "psk_init", "psk_device_count",
     "psk_synchronize", "psk_get_stream", "psk_set_stream", "psk_timer_start", "psk_timer_stop", "psk_launch_count",
-    "psk_live_bytes", "psk_profile", "psk_profile_read", "psk_store_from_runs", "psk_store_from_device_runs", "psk_store_fill",
+    "psk_live_bytes", "psk_profile", "psk_profile_read", "psk_set_jit_threshold", "psk_jit_launch_count", "psk_jit_compile_check", "psk_store_from_runs", "psk_store_from_device_runs", "psk_store_fill",
     "psk_store_from_dense", "psk_store_from_dense_device", "psk_store_to_dense",
     "psk_store_to_dense_device", "psk_store_runs", "psk_store_nruns", "psk_store_span",
     "psk_store_dtype", "psk_store_device_ptrs", "psk_store_first_value", "psk_store_retain",
@@ -177,6 +177,8 @@ class Lib:
         c.psk_version.restype = C.c_char_p
         c.psk_launch_count.restype = C.c_int64
         c.psk_live_bytes.restype = C.c_int64
+        c.psk_jit_launch_count.restype = C.c_int64
+        c.psk_set_jit_threshold.argtypes = [C.c_int64]
         c.psk_store_nruns.restype = C.c_int64
         c.psk_store_nruns.argtypes = [C.c_void_p]
         c.psk_store_span.argtypes = [C.c_void_p]
@@ -244,6 +246,21 @@ class Lib:
 
     def launch_count(self, reset=False) -> int:
         return self.c.psk_launch_count(1 if reset else 0)
+
+    def set_jit_threshold(self, min_total_runs: int):
+        self._chk(self.c.psk_set_jit_threshold(C.c_int64(min_total_runs)))
+
+    def jit_compile_check(self, k: int, prog):
+        """-> (ok, log): NVRTC-compile the kernel specialised for `prog` (no GPU needed)."""
+        nodes = (Node * len(prog))()
+        for i, (op, arg) in enumerate(prog):
+            nodes[i].op, nodes[i].arg = int(op), int(arg) & 0xFFFFFFFF
+        log = C.create_string_buffer(1 << 16)
+        rc = self.c.psk_jit_compile_check(k, len(prog), nodes, log, len(log))
+        return rc == 0, log.value.decode(errors="replace")
+
+    def jit_launch_count(self) -> int:
+        return self.c.psk_jit_launch_count()
 
     def profile(self, enable: bool):
         self._chk(self.c.psk_profile(1 if enable else 0))

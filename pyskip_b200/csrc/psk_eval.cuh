@@ -35,6 +35,30 @@ constexpr int kTileThreads = 256;
 constexpr int kTileCap = 6144;  // runs of all sources staged per tile (excl. look-ahead)
 constexpr int kSentinel = 0x7fffffff;
 
+// Development aid (-DPSK_PHASE_TIMING, tools/phase_profile.py): thread 0 of every CTA adds the
+// clock64() cycles it spends in each phase of the tile loop to p->phase[].  Not compiled into
+// the product library.
+#ifdef PSK_PHASE_TIMING
+#define PSK_PHASE_DECL long long ph_t = clock64(); long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PSK_PHASE(i)                                   \
+  do {                                                 \
+    if (threadIdx.x == 0) {                            \
+      long long now_ = clock64();                      \
+      ph_acc[i] += now_ - ph_t;                        \
+      ph_t = now_;                                     \
+    }                                                  \
+  } while (0)
+#define PSK_PHASE_FLUSH                                                                      \
+  do {                                                                                       \
+    if (threadIdx.x == 0)                                                                    \
+      for (int q_ = 0; q_ < 8; ++q_) atomicAdd(&p->phase[q_], (unsigned long long)ph_acc[q_]); \
+  } while (0)
+#else
+#define PSK_PHASE_DECL
+#define PSK_PHASE(i)
+#define PSK_PHASE_FLUSH
+#endif
+
 // first index in [lo, hi) whose mapped end is > key   (upper bound)
 PSK_D int32_t ub_mapped(const DSource& s, int32_t lo, int32_t hi, int32_t key) {
   while (lo < hi) {
@@ -173,22 +197,36 @@ PSK_D int32_t block_exclusive_scan(int32_t v, int32_t* s_warp /*[T/32+1]*/, int3
 // Look-back chain word: (status << 32) | count.
 enum { ST_INVALID = 0, ST_AGGREGATE = 1, ST_PREFIX = 2 };
 
-PSK_D int32_t lookback_exclusive(unsigned long long* state, int32_t tile, int32_t count) {
+// Decoupled look-back, executed by one full warp: lane l inspects tile (j - l); the nearest
+// tile that already published an inclusive PREFIX ends the walk, the AGGREGATEs in front of
+// it are summed.  Tiles are handed out by an atomic ticket, so every predecessor is resident
+// or finished and the spin cannot deadlock.
+PSK_D int32_t lookback_exclusive_warp(unsigned long long* state, int32_t tile, int32_t count) {
+  const int lane = threadIdx.x & 31;
   if (tile == 0) {
-    st_volatile_u64(&state[0], ((unsigned long long)ST_PREFIX << 32) | (uint32_t)count);
+    if (lane == 0) st_volatile_u64(&state[0], ((unsigned long long)ST_PREFIX << 32) | (uint32_t)count);
     return 0;
   }
-  st_volatile_u64(&state[tile], ((unsigned long long)ST_AGGREGATE << 32) | (uint32_t)count);
+  if (lane == 0) st_volatile_u64(&state[tile], ((unsigned long long)ST_AGGREGATE << 32) | (uint32_t)count);
   int32_t excl = 0;
-  for (int32_t j = tile - 1;; --j) {
-    unsigned long long w;
-    do {
-      w = ld_volatile_u64(&state[j]);
-    } while ((w >> 32) == ST_INVALID);
-    excl += (int32_t)(uint32_t)w;
-    if ((w >> 32) == ST_PREFIX) break;
+  for (int32_t j = tile - 1;; j -= 32) {
+    const int32_t idx = j - lane;
+    unsigned long long w = (unsigned long long)ST_PREFIX << 32;  // virtual prefix 0 before tile 0
+    if (idx >= 0) {
+      do {
+        w = ld_volatile_u64(&state[idx]);
+      } while ((w >> 32) == ST_INVALID);
+    }
+    const unsigned pmask = __ballot_sync(0xffffffffu, (w >> 32) == ST_PREFIX);
+    const int first = pmask ? (__ffs((int)pmask) - 1) : 32;
+    int32_t c = (lane <= first) ? (int32_t)(uint32_t)w : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    excl += c;
+    if (pmask) break;
   }
-  st_volatile_u64(&state[tile], ((unsigned long long)ST_PREFIX << 32) | (uint32_t)(excl + count));
+  if (lane == 0)
+    st_volatile_u64(&state[tile], ((unsigned long long)ST_PREFIX << 32) | (uint32_t)(excl + count));
   return excl;
 }
 
@@ -228,11 +266,13 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
   const int32_t span = p->span;
   const int32_t n_tiles = p->n_tiles;
 
+  PSK_PHASE_DECL;
   for (;;) {
     if (tid == 0) s_tile = atomicAdd(&p->ctrl[CTRL_TICKET], 1);
     __syncthreads();
     const int32_t tile = s_tile;
     if (tile >= n_tiles) break;
+    PSK_PHASE(0);
     const int32_t lo = tile == 0 ? 0 : p->tile_hi[tile - 1];
     const int32_t hi = p->tile_hi[tile];
     if (tid < k) {
@@ -303,6 +343,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
       }
       __syncthreads();
     }
+    PSK_PHASE(1);  // staging
     const bool fail = s_fail != 0;
     if (fail && tid == 0) p->ctrl[CTRL_ERROR] = 1;
 
@@ -335,6 +376,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
       }
     }
 
+    PSK_PHASE(2);  // per-thread binary searches
     // ---- sequential k-way merge over (c0, c1] -------------------------------------------
     int32_t n = 0;
     bool have = false;
@@ -376,11 +418,16 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
     }
 
     // ---- compaction: block scan, cross-tile look-back, coalesced write -------------------
+    PSK_PHASE(3);  // thread 0's own merge loop
     int32_t tile_total;
     const int32_t my_ofs = block_exclusive_scan<T>(n, s_warp, &tile_total);
-    if (tid == 0) {
-      s_gofs = lookback_exclusive(p->tile_state, tile, tile_total);
-      if (tile == n_tiles - 1) p->ctrl[CTRL_COUNT] = s_gofs + tile_total;
+    PSK_PHASE(4);  // waiting for the slowest thread + scan
+    if (tid < 32) {
+      const int32_t excl = lookback_exclusive_warp(p->tile_state, tile, tile_total);
+      if (tid == 0) {
+        s_gofs = excl;
+        if (tile == n_tiles - 1) p->ctrl[CTRL_COUNT] = excl + tile_total;
+      }
     }
     // inE/inV are dead (every thread passed the scan's barriers): reuse them as the
     // compacted staging area so that the global write is fully coalesced
@@ -389,6 +436,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
       inV[my_ofs + j] = outV[base + j];
     }
     __syncthreads();
+    PSK_PHASE(5);  // look-back + smem compaction
     const int32_t gofs = s_gofs;
     if (gofs + tile_total <= p->out_capacity) {
       for (int32_t j = tid; j < tile_total; j += T) {
@@ -399,7 +447,9 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
       p->ctrl[CTRL_ERROR] = 2;
     }
     __syncthreads();
+    PSK_PHASE(6);  // coalesced global write
   }
+  PSK_PHASE_FLUSH;
 }
 
 template <int K>
@@ -412,8 +462,6 @@ __global__ void __launch_bounds__(kTileThreads) k_merge_eval_interp(DPlan* p) {
   merge_eval_tile_loop<K>(p, smem_raw, ev);
 }
 
-constexpr size_t merge_eval_smem_bytes() {
-  return (size_t)(2 * (kTileCap + PSK_MAX_SOURCES) + 2 * kTileCap) * 4;
-}
+constexpr unsigned kMergeEvalSmemBytes = (2 * (kTileCap + PSK_MAX_SOURCES) + 2 * kTileCap) * 4;
 
 }  // namespace psk

@@ -11,7 +11,7 @@
 #include "../../include/pskb200.h"
 #include "psk_platform.h"
 
-#ifndef PSK_CPU_SIM
+#if !defined(PSK_CPU_SIM) && !defined(__CUDACC_RTC__)
 #include <math.h>
 #endif
 

@@ -58,6 +58,7 @@ struct DPlan {
   int32_t* tile_hi;                // [max_tiles] inclusive upper coordinate of each tile
   unsigned long long* tile_state;  // [max_tiles] look-back chain
   int32_t* ctrl;                   // [0]=ticket [1]=out_count [2]=error
+  unsigned long long* phase;       // [8] cycle counters (PSK_PHASE_TIMING builds only)
   int32_t* out_ends;
   uint32_t* out_vals;
   psk_node prog[PSK_MAX_PROGRAM];

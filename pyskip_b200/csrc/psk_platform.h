@@ -4,7 +4,9 @@
 // loaded by the package -- see DESIGN.md "Kernel simulator").
 #pragma once
 
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#endif
 
 #ifdef PSK_CPU_SIM
 #include "cuda_sim.h"
@@ -14,7 +16,9 @@
 #define PSK_HD inline
 #define PSK_D inline
 #else
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 #define PSK_LAUNCH(kernel, grid, block, smem, stream, ...) \
   kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define PSK_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]

@@ -18,6 +18,9 @@
 
 #include "psk_convert.cuh"
 #include "psk_eval.cuh"
+#ifndef PSK_CPU_SIM
+#include "psk_jit.h"
+#endif
 
 using namespace psk;
 
@@ -46,6 +49,9 @@ struct Ctx {
   double prof_ms = 0.0;
   int64_t prof_n = 0;
   int64_t prof_runs_in = 0, prof_runs_out = 0;
+  unsigned long long phase_cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t jit_min_runs = 1 << 18;  // evaluations at least this large get a specialised kernel
+  int64_t jit_launches = 0;
   DPlan* h_plan = nullptr;      // pinned staging copy of the plan
   int32_t* h_ctrl = nullptr;    // pinned read-back of CTRL words / small results
   std::atomic<int64_t> launches{0};
@@ -113,7 +119,7 @@ psk_status do_init(int device) {
     }
   }
 #endif
-  const int smem = (int)merge_eval_smem_bytes();
+  const int smem = (int)kMergeEvalSmemBytes;
   CUDA_TRY(cudaFuncSetAttribute(k_merge_eval_interp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CUDA_TRY(cudaFuncSetAttribute(k_merge_eval_interp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CUDA_TRY(cudaFuncSetAttribute(k_merge_eval_interp<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -208,7 +214,7 @@ void dview_spans(const DView& d, int64_t* in, int64_t* out) {
 int pick_K(int k) { return k <= 2 ? 2 : k <= 4 ? 4 : k <= 8 ? 8 : k <= 16 ? 16 : 32; }
 
 void launch_merge_eval(int K, int grid, DPlan* d_plan) {
-  const size_t smem = merge_eval_smem_bytes();
+  const size_t smem = kMergeEvalSmemBytes;
   switch (K) {
     case 2: LAUNCH(k_merge_eval_interp<2>, grid, kTileThreads, smem, d_plan); break;
     case 4: LAUNCH(k_merge_eval_interp<4>, grid, kTileThreads, smem, d_plan); break;
@@ -384,6 +390,23 @@ int64_t psk_launch_count(int32_t reset) {
 
 int64_t psk_live_bytes(void) { return g.live_bytes.load(); }
 
+psk_status psk_set_jit_threshold(int64_t min_total_runs) {
+  g.jit_min_runs = min_total_runs;
+  return PSK_OK;
+}
+
+int64_t psk_jit_launch_count(void) { return g.jit_launches; }
+
+int32_t psk_jit_compile_check(int32_t k, int32_t nprog, const psk_node* prog, char* log, int32_t loglen) {
+#ifdef PSK_CPU_SIM
+  (void)k; (void)nprog; (void)prog; (void)log; (void)loglen;
+  return -1;
+#else
+  if (validate_program(k, nprog, prog) != PSK_OK) return 2;
+  return jit_compile_check(pick_K(k), nprog, prog, log, loglen);
+#endif
+}
+
 psk_status psk_profile(int32_t enable) {
   g.profile = enable != 0;
   g.prof_ms = 0.0;
@@ -391,6 +414,16 @@ psk_status psk_profile(int32_t enable) {
   g.prof_runs_in = g.prof_runs_out = 0;
   return PSK_OK;
 }
+
+#ifdef PSK_PHASE_TIMING
+// development builds only (tools/phase_profile.py); not part of include/pskb200.h
+PSK_API void psk_phase_read(unsigned long long* out8, int32_t reset) {
+  for (int q = 0; q < 8; ++q) {
+    out8[q] = g.phase_cycles[q];
+    if (reset) g.phase_cycles[q] = 0;
+  }
+}
+#endif
 
 psk_status psk_profile_read(double* merge_eval_ms, int64_t* evals, int64_t* runs_in, int64_t* runs_out) {
   PSK_CHECK_ARG(merge_eval_ms && evals && runs_in && runs_out);
@@ -702,7 +735,8 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
 
   // ---- scratch: [tile_state | ctrl | merged | bounds | tile_hi | plan] --------------------
   size_t o_state = 0;
-  size_t o_ctrl = o_state + (size_t)max_tiles * 8;
+  size_t o_phase = o_state + (size_t)max_tiles * 8;
+  size_t o_ctrl = o_phase + 8 * 8;
   size_t o_merged = o_ctrl + CTRL_WORDS * 4;
   size_t o_bounds = o_merged + (size_t)max_samples * 4;
   size_t o_hi = o_bounds + (size_t)(max_tiles + 1) * k * 4;
@@ -720,6 +754,7 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
   }
   hp.tile_state = reinterpret_cast<unsigned long long*>(scratch + o_state);
   hp.ctrl = reinterpret_cast<int32_t*>(scratch + o_ctrl);
+  hp.phase = reinterpret_cast<unsigned long long*>(scratch + o_phase);
   hp.merged = reinterpret_cast<int32_t*>(scratch + o_merged);
   hp.bounds = reinterpret_cast<int32_t*>(scratch + o_bounds);
   hp.tile_hi = reinterpret_cast<int32_t*>(scratch + o_hi);
@@ -737,11 +772,27 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
     int64_t grid = 2 * (int64_t)g.sm_count;
     if (grid > max_tiles) grid = max_tiles;
     if (g.profile) cudaEventRecord(g.pev0, g.stream);
-    launch_merge_eval(pick_K(k), (int)grid, d_plan);
+    bool launched = false;
+#ifndef PSK_CPU_SIM
+    if (total_runs >= g.jit_min_runs) {
+      // the same kernel template with the program compiled in (psk_jit.h)
+      if (const JitKernel* jk = jit_get_merge_eval(pick_K(k), nprog, prog, nullptr)) {
+        if (jit_launch(jk, (unsigned)grid, kTileThreads, kMergeEvalSmemBytes, g.stream, d_plan) == 0) {
+          launched = true;
+          g.launches.fetch_add(1, std::memory_order_relaxed);
+          g.jit_launches += 1;
+        }
+      }
+    }
+#endif
+    if (!launched) launch_merge_eval(pick_K(k), (int)grid, d_plan);
     if (g.profile) cudaEventRecord(g.pev1, g.stream);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(g.h_ctrl, hp.ctrl, CTRL_WORDS * 4, cudaMemcpyDeviceToHost, g.stream);
+#ifdef PSK_PHASE_TIMING
+  if (e == cudaSuccess) e = cudaMemcpyAsync(g.h_ctrl + 16, hp.phase, 64, cudaMemcpyDeviceToHost, g.stream);
+#endif
   if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
   cudaFreeAsync(scratch, g.stream);
   if (e != cudaSuccess) {
@@ -754,6 +805,9 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
   }
   res->nruns = g.h_ctrl[CTRL_COUNT];
   res->span = (int32_t)span;
+#ifdef PSK_PHASE_TIMING
+  for (int q = 0; q < 8; ++q) g.phase_cycles[q] += reinterpret_cast<unsigned long long*>(g.h_ctrl + 16)[q];
+#endif
   if (g.profile) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, g.pev0, g.pev1) == cudaSuccess) {

@@ -196,3 +196,52 @@ def test_arg_errors(lib):
         lib.store_from_runs(np.array([3, 3], np.int32), np.array([1, 2], np.int32))
     with pytest.raises(ValueError):
         lib.store_fill(A.I32, 0, 1)       # core.hpp:106 span > 0
+
+
+@pytest.mark.gpu
+def test_jit_matches_interpreter_and_oracle():
+    """The NVRTC-specialised kernel (large evaluations) and the generic interpreter kernel
+    must produce identical stores."""
+    from helpers import cuda_lib
+    lib = cuda_lib()
+    rng = np.random.default_rng(77)
+    span = 3_000_000
+    srcs = [rand_runs(rng, span, 40_000, np.float32, 0, 64) + ([],) for _ in range(4)]
+    a, b, c, d = [("src", i) for i in range(4)]
+    expr = ("sub", ("max", ("add", ("mul", a, b), c), d), ("mul", ("sqrt", ("abs", a)), ("const", 0.5, np.float32)))
+    want = oracle_eval(srcs, expr, "typed")
+    try:
+        lib.set_jit_threshold(0)
+        n0 = lib.jit_launch_count()
+        got_jit = run_eval(lib, srcs, expr, "typed")
+        assert lib.jit_launch_count() == n0 + 1, "specialised kernel was not used"
+        lib.set_jit_threshold(-1 if False else 1 << 62)
+        got_int = run_eval(lib, srcs, expr, "typed")
+        assert lib.jit_launch_count() == n0 + 1
+    finally:
+        lib.set_jit_threshold(1 << 18)
+    assert_runs_equal(got_jit, want, "jit")
+    assert_runs_equal(got_int, want, "interp")
+    # int program with a view and k = 9 sources through the specialised kernel
+    isrcs = [rand_runs(rng, 500_000, 9_000) + ([],) for _ in range(9)]
+    e = ("src", 0)
+    for i in range(1, 9):
+        e = ("add", e, ("mul", ("src", i), ("const", i + 1, np.int32)))
+    try:
+        lib.set_jit_threshold(0)
+        got = run_eval(lib, isrcs, e)
+    finally:
+        lib.set_jit_threshold(1 << 18)
+    assert_runs_equal(got, oracle_eval(isrcs, e), "jit k=9")
+
+
+def test_jit_source_compiles_for_sm100a():
+    """CPU-side check (needs libnvrtc, no GPU): the specialised kernel source compiles."""
+    from pyskip_b200 import _abi
+    lib = _abi.lib()
+    F = A.OP_F
+    prog = [(A.OP_SRC, 0), (A.OP_SRC, 1), (F["mul"], 0), (A.OP_SRC, 2), (F["add"], 0), (A.OP_CONST, 5), (F["max"], 0)]
+    ok, log = lib.jit_compile_check(3, prog)
+    if not ok and "libnvrtc not found" in log:
+        pytest.skip("libnvrtc not installed")
+    assert ok, log[:2000]

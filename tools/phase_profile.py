@@ -1,0 +1,45 @@
+"""Development tool: per-phase cycle breakdown of k_merge_eval on the bench workload.
+Builds a -DPSK_PHASE_TIMING variant of the library next to the product one and runs a few
+evaluations.  Usage (GPU box): python tools/phase_profile.py [scale]"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+from pyskip_b200 import _abi as A, build as B
+import bench
+
+out = os.path.join(ROOT, "gpurun_out", "libpskb200_phase.so")
+os.makedirs(os.path.dirname(out), exist_ok=True)
+if "--build-only" in sys.argv or not os.path.exists(out):
+    subprocess.check_call([B.nvcc_path()] + B.NVCC_FLAGS + ["-DPSK_PHASE_TIMING", "-I" + B.CSRC,
+                          os.path.join(B.CSRC, "pskb200_abi.cu"), os.path.join(B.CSRC, "psk_jit.cpp"),
+                          "-o", out, "-ldl"])
+    if "--build-only" in sys.argv:
+        sys.exit(0)
+scale = float(sys.argv[1]) if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else 1.0
+lib = A.Lib(out)
+lib.init(0)
+n, r = int(bench.N_ELEMS * scale), int(bench.N_RUNS * scale)
+stores = [lib.store_from_runs(*bench.gen_operand(2000 + j, n, r)) for j in range(4)]
+prog = bench.dag_program(A)
+srcs = [(s, []) for s in stores]
+for _ in range(3):
+    lib.eval(srcs, prog, A.F32)
+buf = (C.c_ulonglong * 8)()
+lib.c.psk_phase_read(buf, 1)
+lib.profile(True)
+N = 10
+for _ in range(N):
+    res = lib.eval(srcs, prog, A.F32)
+lib.c.psk_phase_read(buf, 1)
+ms, ne, ri, ro = lib.profile_read()
+tot = sum(buf)
+names = ["ticket+desc", "staging", "thread search", "merge (thread 0)", "wait slowest+scan", "lookback+compact",
+         "global write", "-"]
+print(f"merge_eval avg {ms / ne:.3f} ms; runs in {ri // ne} out {ro // ne}; jit launches {lib.jit_launch_count()}")
+for nm, c in zip(names, buf):
+    print(f"  {nm:22s} {c / max(tot, 1) * 100:6.2f} %   {c / N / 296:12.0f} cycles per CTA per eval")
