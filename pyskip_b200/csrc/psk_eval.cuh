@@ -31,8 +31,14 @@
 
 namespace psk {
 
-constexpr int kTileThreads = 256;
-constexpr int kTileCap = 6144;  // runs of all sources staged per tile (excl. look-ahead)
+#ifndef PSK_TILE_THREADS
+#define PSK_TILE_THREADS 256
+#endif
+#ifndef PSK_TILE_CAP
+#define PSK_TILE_CAP 6144
+#endif
+constexpr int kTileThreads = PSK_TILE_THREADS;
+constexpr int kTileCap = PSK_TILE_CAP;  // runs of all sources staged per tile (excl. look-ahead)
 constexpr int kSentinel = 0x7fffffff;
 
 // Development aid (-DPSK_PHASE_TIMING, tools/phase_profile.py): thread 0 of every CTA adds the
@@ -244,69 +250,149 @@ struct InterpEval {
 
 // ---------------------------------------------------------------------------------------
 // k_merge_eval<K>: K = compile-time bound on the number of sources (heads live in registers).
+//
+// Shared memory per CTA: in[] = the tile's runs as (end, value) pairs, one slice per source
+// plus one look-ahead run each; out[] = the spans each thread keeps.  After the block scan
+// in[] is dead and becomes the compacted staging area for the coalesced global write.
+struct TileDesc {          // bounds of one tile, fetched one tile ahead
+  int32_t tile;
+  int32_t lo, hi;
+  int32_t b0[PSK_MAX_SOURCES];
+  int32_t b1[PSK_MAX_SOURCES];
+};
+
+struct SrcDesc {           // the per-source fields the tile loop needs, hoisted into smem once
+  const int32_t* ends;
+  const uint32_t* vals;
+  int32_t nviews;
+  int32_t e;
+};
+
+// warp 0: take the next ticket and fetch that tile's bounds into *d (no barrier here)
+PSK_D void fetch_tile_desc(DPlan* p, TileDesc* d, int k, int32_t n_tiles) {
+  const int lane = threadIdx.x & 31;
+  int32_t tile = 0;
+  if (lane == 0) tile = atomicAdd(&p->ctrl[CTRL_TICKET], 1);
+  tile = __shfl_sync(0xffffffffu, tile, 0);
+  if (lane == 0) d->tile = tile;
+  if (tile < n_tiles) {
+    if (lane < k) {
+      d->b0[lane] = p->bounds[tile * k + lane];
+      d->b1[lane] = p->bounds[(tile + 1) * k + lane];
+    }
+    if (lane == 0) {
+      d->lo = tile == 0 ? 0 : p->tile_hi[tile - 1];
+      d->hi = p->tile_hi[tile];
+    }
+  }
+}
+
 template <int K, typename Eval>
 PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& ev) {
   constexpr int T = kTileThreads;
   constexpr int CAP = kTileCap;
   constexpr int IN_N = CAP + PSK_MAX_SOURCES;  // room for one look-ahead run per source
 
-  int32_t* inE = reinterpret_cast<int32_t*>(smem_raw);
-  uint32_t* inV = reinterpret_cast<uint32_t*>(inE + IN_N);
-  int32_t* outE = reinterpret_cast<int32_t*>(inV + IN_N);
-  uint32_t* outV = reinterpret_cast<uint32_t*>(outE + CAP);
+  int2* in = reinterpret_cast<int2*>(smem_raw);
+  int2* out = in + IN_N;
 
-  __shared__ int32_t s_off[PSK_MAX_SOURCES + 1];  // start of each source's slice in inE/inV
-  __shared__ int32_t s_b0[PSK_MAX_SOURCES], s_b1[PSK_MAX_SOURCES];
+  __shared__ TileDesc s_desc[2];
+  __shared__ SrcDesc s_src[PSK_MAX_SOURCES];
+  __shared__ int32_t s_off[PSK_MAX_SOURCES + 1];  // start of each source's slice in in[]
+  __shared__ int32_t s_len[PSK_MAX_SOURCES];      // staged runs of each source (excl. look-ahead)
   __shared__ int32_t s_warp[T / 32 + 2];
-  __shared__ int32_t s_tile, s_gofs, s_carry, s_fail;
+  __shared__ int32_t s_gofs, s_carry, s_fail, s_flat_total;
 
   const int tid = threadIdx.x;
   const int k = p->k;
   const bool typed_float = p->eq != 0;
+  const bool any_views = p->any_views != 0;
   const int32_t span = p->span;
   const int32_t n_tiles = p->n_tiles;
 
-  PSK_PHASE_DECL;
-  for (;;) {
-    if (tid == 0) s_tile = atomicAdd(&p->ctrl[CTRL_TICKET], 1);
-    __syncthreads();
-    const int32_t tile = s_tile;
-    if (tile >= n_tiles) break;
-    PSK_PHASE(0);
-    const int32_t lo = tile == 0 ? 0 : p->tile_hi[tile - 1];
-    const int32_t hi = p->tile_hi[tile];
-    if (tid < k) {
-      s_b0[tid] = p->bounds[tile * k + tid];
-      s_b1[tid] = p->bounds[(tile + 1) * k + tid];
-    }
-    if (tid == 0) { s_off[0] = 0; s_fail = 0; }
-    __syncthreads();
+  if (tid < k) {
+    const DSource& s = p->src[tid];
+    s_src[tid].ends = s.ends;
+    s_src[tid].vals = s.vals;
+    s_src[tid].nviews = s.nviews;
+    s_src[tid].e = s.e;
+  }
+  if (tid < 32) fetch_tile_desc(p, &s_desc[0], k, n_tiles);
+  __syncthreads();
 
-    // ---- stage every source's slice [b0, b1) plus one look-ahead run -------------------
-    for (int i = 0; i < k; ++i) {
-      const DSource& s = p->src[i];
-      const int32_t b0 = s_b0[i], b1 = s_b1[i];
-      const int32_t off = s_off[i];
-      int32_t kept;
-      if (s.nviews == 0) {
-        kept = b1 - b0;
-        if (off + kept + 1 <= IN_N) {
-          for (int32_t j = tid; j < kept; j += T) {
-            inE[off + j] = s.ends[b0 + j];
-            inV[off + j] = s.vals[b0 + j];
+  PSK_PHASE_DECL;
+  for (int it = 0;; ++it) {
+    const TileDesc& d = s_desc[it & 1];
+    const int32_t tile = d.tile;
+    if (tile >= n_tiles) break;
+    const int32_t lo = d.lo, hi = d.hi;
+
+    // ---- slice offsets: sources without a view are copied in one flat pass ---------------
+    if (tid < 32) {
+      int32_t len = 0;
+      if (tid < k && s_src[tid].nviews == 0) len = d.b1[tid] - d.b0[tid] + 1;  // + look-ahead
+      int32_t inc = len;
+#pragma unroll
+      for (int dd = 1; dd < 32; dd <<= 1) {
+        int32_t o = __shfl_up_sync(0xffffffffu, inc, dd);
+        if (tid >= dd) inc += o;
+      }
+      if (tid < k) {
+        s_off[tid] = inc - len;
+        s_len[tid] = len ? len - 1 : 0;
+      }
+      if (tid == 31) s_flat_total = inc;
+      if (tid == 0) s_fail = 0;
+    } else if (tid < 64) {
+      // meanwhile warp 1 takes the next ticket and fetches the next tile's bounds
+      fetch_tile_desc(p, &s_desc[(it + 1) & 1], k, n_tiles);
+    }
+    __syncthreads();
+    PSK_PHASE(0);
+    int32_t used = s_flat_total;
+    bool fail = used > IN_N;
+    if (!fail) {
+      for (int32_t j = tid; j < used; j += T) {
+        // which source owns flat slot j: last i with s_off[i] <= j among the view-less sources
+        int i = 0;
+        {
+          int l = 0, h = k - 1;
+          while (l < h) {  // s_off is non-decreasing over i (view sources have length 0)
+            int mid = (l + h + 1) >> 1;
+            if (s_off[mid] <= j) l = mid; else h = mid - 1;
           }
+          i = l;
+          while (s_src[i].nviews != 0 || j - s_off[i] > s_len[i]) --i;  // skip zero-length slots
         }
-      } else {
-        // mapped ends; a run whose mapped end equals its predecessor's is empty -> dropped
+        const int32_t r = j - s_off[i];
+        const int32_t idx = d.b0[i] + r;
+        int2 pr;
+        if (r < s_len[i] || idx < s_src[i].e) {
+          pr.x = s_src[i].ends[idx];
+          pr.y = (int32_t)s_src[i].vals[idx];
+        } else {  // no run beyond the tile: sentinel look-ahead
+          pr.x = kSentinel;
+          pr.y = 0;
+        }
+        in[j] = pr;
+      }
+    }
+    // ---- sources with a view: mapped ends, zero-length mapped runs dropped ---------------
+    if (any_views && !fail) {
+      for (int i = 0; i < k; ++i) {
+        if (s_src[i].nviews == 0) continue;  // uniform branch
+        const DSource& s = p->src[i];
+        const int32_t b0 = d.b0[i], b1 = d.b1[i];
+        const int32_t off = used;
+        int32_t kept = 0;
+        __syncthreads();
         if (tid == 0) s_carry = lo;
-        kept = 0;
         for (int32_t base = b0; base < b1; base += T) {
           __syncthreads();
           const int32_t idx = base + tid;
           const bool valid = idx < b1;
           const int32_t me = valid ? map_chain(s.v, s.nviews, s.ends[idx]) : kSentinel;
-          // predecessor's mapped end: previous lane, previous warp's last lane, or carry
-          int32_t* s_last = s_warp;  // reuse: [T/32] last mapped end of each warp
+          int32_t* s_last = s_warp;  // [T/32] last mapped end of each warp
           int32_t pm = __shfl_up_sync(0xffffffffu, me, 1);
           if ((tid & 31) == 31) s_last[tid >> 5] = me;
           __syncthreads();
@@ -315,36 +401,25 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
           __syncthreads();  // s_last consumed before the scan reuses s_warp
           int32_t tot;
           const int32_t pos = block_exclusive_scan<T>(keep ? 1 : 0, s_warp, &tot);
-          if (keep && off + kept + pos < IN_N) {
-            inE[off + kept + pos] = me;
-            inV[off + kept + pos] = s.vals[idx];
-          }
+          if (keep && off + kept + pos < IN_N) in[off + kept + pos] = make_int2(me, (int32_t)s.vals[idx]);
           kept += tot;
-          // carry = mapped end of the last valid run of this chunk
           const int32_t last_valid = (b1 - base < T ? b1 - base : T) - 1;
           if (tid == last_valid) s_carry = me;
         }
-        __syncthreads();
-      }
-      if (tid == 0) {
         if (off + kept + 1 > IN_N) {
-          s_fail = 1;
-          kept = 0;
+          fail = true;  // uniform: every thread sees the same kept
+          break;
         }
-        // look-ahead: the first run beyond the tile (its mapped end is > hi) or a sentinel
-        if (b1 < s.e) {
-          inE[off + kept] = mapped_end(s, b1);
-          inV[off + kept] = s.vals[b1];
-        } else {
-          inE[off + kept] = kSentinel;
-          inV[off + kept] = 0;
+        if (tid == 0) {
+          in[off + kept] = (b1 < s.e) ? make_int2(mapped_end(s, b1), (int32_t)s.vals[b1]) : make_int2(kSentinel, 0);
+          s_off[i] = off;
+          s_len[i] = kept;
         }
-        s_off[i + 1] = off + kept + 1;
+        used = off + kept + 1;
       }
-      __syncthreads();
     }
+    __syncthreads();
     PSK_PHASE(1);  // staging
-    const bool fail = s_fail != 0;
     if (fail && tid == 0) p->ctrl[CTRL_ERROR] = 1;
 
     // ---- split the tile's coordinate range (lo, hi] over the threads --------------------
@@ -352,25 +427,40 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
     const int32_t c0 = lo + (int32_t)((width * tid) / T);
     const int32_t c1 = lo + (int32_t)((width * (tid + 1)) / T);
 
-    int32_t cur[K], head[K];
+    // first staged run of every source whose end is > c0: branch-free binary searches that
+    // advance in lock step over the sources (the look-ahead run bounds each of them)
+    int32_t cur[K], head[K], rem[K];
     uint32_t val[K];
     int32_t base = 0;
 #pragma unroll
     for (int i = 0; i < K; ++i) {
-      if (i < k && !fail) {
-        // first staged run of source i whose end is > c0 (the look-ahead run bounds it)
-        int32_t l = s_off[i], h = s_off[i + 1] - 1;
-        const int32_t first = l;
-        while (l < h) {
-          int32_t mid = l + ((h - l) >> 1);
-          if (inE[mid] <= c0) l = mid + 1; else h = mid;
+      cur[i] = (i < k) ? s_off[i] : 0;
+      rem[i] = (i < k && !fail) ? s_len[i] + 1 : 1;
+    }
+    {
+      int32_t longest = 1;
+#pragma unroll
+      for (int i = 0; i < K; ++i) longest = imax(longest, rem[i]);
+      for (; longest > 1; longest -= longest >> 1) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          const int32_t half = rem[i] >> 1;
+          if (half > 0) {
+            const bool right = in[cur[i] + half - 1].x <= c0;
+            cur[i] += right ? half : 0;
+            rem[i] -= half;
+          }
         }
-        cur[i] = l;
-        head[i] = inE[l];
-        val[i] = inV[l];
-        base += l - first;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      if (i < k && !fail) {
+        const int2 pr = in[cur[i]];
+        head[i] = pr.x;
+        val[i] = (uint32_t)pr.y;
+        base += cur[i] - s_off[i];
       } else {
-        cur[i] = 0;
         head[i] = kSentinel;
         val[i] = 0;
       }
@@ -378,30 +468,44 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
 
     PSK_PHASE(2);  // per-thread binary searches
     // ---- sequential k-way merge over (c0, c1] -------------------------------------------
+    // One run is consumed per iteration (one 64-bit shared load per lane); sources that
+    // share an end are drained by further iterations that see e == last_e and emit nothing.
     int32_t n = 0;
     bool have = false;
-    int32_t pe = 0;
+    int32_t pe = 0, last_e = c0;
     uint32_t pv = 0;
     for (;;) {
       int32_t e = head[0];
 #pragma unroll
       for (int i = 1; i < K; ++i) e = imin(e, head[i]);
       if (e > c1) break;
-      const uint32_t v = ev(val);  // value of the span that ends at e
-      if (have && !payload_equal(pv, v, typed_float)) {
-        outE[base + n] = pe;
-        outV[base + n] = pv;
-        ++n;
+      if (e != last_e) {
+        const uint32_t v = ev(val);  // value of the span that ends at e
+        if (have && !payload_equal(pv, v, typed_float)) {
+          out[base + n] = make_int2(pe, (int32_t)pv);
+          ++n;
+        }
+        pe = e;
+        pv = v;
+        have = true;
+        last_e = e;
       }
-      pe = e;
-      pv = v;
-      have = true;
+      int32_t idx = 0;
+      int j = K;
+#pragma unroll
+      for (int i = K - 1; i >= 0; --i) {
+        if (head[i] == e) {
+          j = i;
+          idx = cur[i];
+        }
+      }
+      const int2 nx = in[idx + 1];
 #pragma unroll
       for (int i = 0; i < K; ++i) {
-        if (head[i] == e) {
-          ++cur[i];
-          head[i] = inE[cur[i]];
-          val[i] = inV[cur[i]];
+        if (i == j) {
+          cur[i] = idx + 1;
+          head[i] = nx.x;
+          val[i] = (uint32_t)nx.y;
         }
       }
     }
@@ -411,14 +515,13 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
       bool keep = (pe == span);
       if (!keep) keep = !payload_equal(pv, ev(val), typed_float);
       if (keep) {
-        outE[base + n] = pe;
-        outV[base + n] = pv;
+        out[base + n] = make_int2(pe, (int32_t)pv);
         ++n;
       }
     }
 
-    // ---- compaction: block scan, cross-tile look-back, coalesced write -------------------
     PSK_PHASE(3);  // thread 0's own merge loop
+    // ---- compaction: block scan, cross-tile look-back, coalesced write -------------------
     int32_t tile_total;
     const int32_t my_ofs = block_exclusive_scan<T>(n, s_warp, &tile_total);
     PSK_PHASE(4);  // waiting for the slowest thread + scan
@@ -429,19 +532,17 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
         if (tile == n_tiles - 1) p->ctrl[CTRL_COUNT] = excl + tile_total;
       }
     }
-    // inE/inV are dead (every thread passed the scan's barriers): reuse them as the
-    // compacted staging area so that the global write is fully coalesced
-    for (int32_t j = 0; j < n; ++j) {
-      inE[my_ofs + j] = outE[base + j];
-      inV[my_ofs + j] = outV[base + j];
-    }
+    // in[] is dead (every thread passed the scan's barriers): reuse it as the compacted
+    // staging area so that the global write is fully coalesced
+    for (int32_t j = 0; j < n; ++j) in[my_ofs + j] = out[base + j];
     __syncthreads();
     PSK_PHASE(5);  // look-back + smem compaction
     const int32_t gofs = s_gofs;
     if (gofs + tile_total <= p->out_capacity) {
       for (int32_t j = tid; j < tile_total; j += T) {
-        p->out_ends[gofs + j] = inE[j];
-        p->out_vals[gofs + j] = inV[j];
+        const int2 r = in[j];
+        p->out_ends[gofs + j] = r.x;
+        p->out_vals[gofs + j] = (uint32_t)r.y;
       }
     } else if (tid == 0) {
       p->ctrl[CTRL_ERROR] = 2;
@@ -462,6 +563,6 @@ __global__ void __launch_bounds__(kTileThreads) k_merge_eval_interp(DPlan* p) {
   merge_eval_tile_loop<K>(p, smem_raw, ev);
 }
 
-constexpr unsigned kMergeEvalSmemBytes = (2 * (kTileCap + PSK_MAX_SOURCES) + 2 * kTileCap) * 4;
+constexpr unsigned kMergeEvalSmemBytes = ((kTileCap + PSK_MAX_SOURCES) + kTileCap) * 8;
 
 }  // namespace psk

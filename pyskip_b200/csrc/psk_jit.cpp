@@ -17,6 +17,9 @@
 // pyskip_b200/build.py so that NVRTC sees exactly the sources nvcc compiled.
 #include "_jit_embed.inc"
 
+#define PSK_STR2(x) #x
+#define PSK_STR(x) PSK_STR2(x)
+
 namespace psk {
 namespace {
 
@@ -197,6 +200,12 @@ bool compile_cubin(int K, int nprog, const psk_node* prog, std::vector<char>* cu
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo",
 #ifdef PSK_PHASE_TIMING
                         "-DPSK_PHASE_TIMING",
+#endif
+#ifdef PSK_TILE_THREADS
+                        "-DPSK_TILE_THREADS=" PSK_STR(PSK_TILE_THREADS),
+#endif
+#ifdef PSK_TILE_CAP
+                        "-DPSK_TILE_CAP=" PSK_STR(PSK_TILE_CAP),
 #endif
   };
   r = g_api.nvrtcCompileProgram(np, (int)(sizeof(opts) / sizeof(opts[0])), opts);

@@ -38,6 +38,11 @@
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
 
+struct int2 {
+  int x, y;
+};
+inline int2 make_int2(int x, int y) { return int2{x, y}; }
+
 struct psk_sim_uint3 {
   unsigned x = 0, y = 0, z = 0;
 };

@@ -12,15 +12,29 @@ import numpy as np
 from pyskip_b200 import _abi as A, build as B
 import bench
 
-out = os.path.join(ROOT, "gpurun_out", "libpskb200_phase.so")
+import argparse
+ap = argparse.ArgumentParser()
+ap.add_argument("--threads", type=int, default=0)
+ap.add_argument("--cap", type=int, default=0)
+ap.add_argument("--scale", type=float, default=1.0)
+ap.add_argument("--build-only", action="store_true")
+ap.add_argument("--no-phase", action="store_true")
+args = ap.parse_args()
+defs = [] if args.no_phase else ["-DPSK_PHASE_TIMING"]
+if args.threads:
+    defs.append(f"-DPSK_TILE_THREADS={args.threads}")
+if args.cap:
+    defs.append(f"-DPSK_TILE_CAP={args.cap}")
+out = os.path.join(ROOT, "gpurun_out", f"libpskb200_phase_{args.threads}_{args.cap}_{int(args.no_phase)}.so")
 os.makedirs(os.path.dirname(out), exist_ok=True)
-if "--build-only" in sys.argv or not os.path.exists(out):
-    subprocess.check_call([B.nvcc_path()] + B.NVCC_FLAGS + ["-DPSK_PHASE_TIMING", "-I" + B.CSRC,
+if args.build_only or not os.path.exists(out):
+    B.gen_jit_embed()
+    subprocess.check_call([B.nvcc_path()] + B.NVCC_FLAGS + defs + ["-I" + B.CSRC,
                           os.path.join(B.CSRC, "pskb200_abi.cu"), os.path.join(B.CSRC, "psk_jit.cpp"),
                           "-o", out, "-ldl"])
-    if "--build-only" in sys.argv:
+    if args.build_only:
         sys.exit(0)
-scale = float(sys.argv[1]) if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else 1.0
+scale = args.scale
 lib = A.Lib(out)
 lib.init(0)
 n, r = int(bench.N_ELEMS * scale), int(bench.N_RUNS * scale)
@@ -30,16 +44,19 @@ srcs = [(s, []) for s in stores]
 for _ in range(3):
     lib.eval(srcs, prog, A.F32)
 buf = (C.c_ulonglong * 8)()
-lib.c.psk_phase_read(buf, 1)
+if not args.no_phase:
+    lib.c.psk_phase_read(buf, 1)
 lib.profile(True)
 N = 10
 for _ in range(N):
     res = lib.eval(srcs, prog, A.F32)
-lib.c.psk_phase_read(buf, 1)
+if not args.no_phase:
+    lib.c.psk_phase_read(buf, 1)
 ms, ne, ri, ro = lib.profile_read()
 tot = sum(buf)
 names = ["ticket+desc", "staging", "thread search", "merge (thread 0)", "wait slowest+scan", "lookback+compact",
          "global write", "-"]
+print(f"threads {args.threads or 256} cap {args.cap or 6144}")
 print(f"merge_eval avg {ms / ne:.3f} ms; runs in {ri // ne} out {ro // ne}; jit launches {lib.jit_launch_count()}")
 for nm, c in zip(names, buf):
     print(f"  {nm:22s} {c / max(tot, 1) * 100:6.2f} %   {c / N / 296:12.0f} cycles per CTA per eval")
