@@ -352,29 +352,37 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
     int32_t used = s_flat_total;
     bool fail = used > IN_N;
     if (!fail) {
-      for (int32_t j = tid; j < used; j += T) {
-        // which source owns flat slot j: last i with s_off[i] <= j among the view-less sources
-        int i = 0;
-        {
-          int l = 0, h = k - 1;
-          while (l < h) {  // s_off is non-decreasing over i (view sources have length 0)
-            int mid = (l + h + 1) >> 1;
-            if (s_off[mid] <= j) l = mid; else h = mid - 1;
+      // All global loads of a batch are issued before any shared store (ld.global.nc cannot
+      // alias the staging buffer), so a thread keeps kStageBatch x 2 loads in flight.
+      constexpr int kStageBatch = 8;
+      for (int32_t j0 = tid; j0 < used; j0 += T * kStageBatch) {
+        int2 pr[kStageBatch];
+#pragma unroll
+        for (int u = 0; u < kStageBatch; ++u) {
+          const int32_t j = j0 + u * T;
+          pr[u] = make_int2(kSentinel, 0);  // no run beyond the tile: sentinel look-ahead
+          if (j < used) {
+            // which source owns flat slot j: last i with s_off[i] <= j (view sources have
+            // zero slots here and are never the last such i)
+            int l = 0, h = k - 1;
+            while (l < h) {
+              int mid = (l + h + 1) >> 1;
+              if (s_off[mid] <= j) l = mid; else h = mid - 1;
+            }
+            const int i = l;
+            const int32_t r = j - s_off[i];
+            const int32_t idx = d.b0[i] + r;
+            if (r < s_len[i] || idx < s_src[i].e) {
+              pr[u].x = ld_nc(s_src[i].ends + idx);
+              pr[u].y = (int32_t)ld_nc(s_src[i].vals + idx);
+            }
           }
-          i = l;
-          while (s_src[i].nviews != 0 || j - s_off[i] > s_len[i]) --i;  // skip zero-length slots
         }
-        const int32_t r = j - s_off[i];
-        const int32_t idx = d.b0[i] + r;
-        int2 pr;
-        if (r < s_len[i] || idx < s_src[i].e) {
-          pr.x = s_src[i].ends[idx];
-          pr.y = (int32_t)s_src[i].vals[idx];
-        } else {  // no run beyond the tile: sentinel look-ahead
-          pr.x = kSentinel;
-          pr.y = 0;
+#pragma unroll
+        for (int u = 0; u < kStageBatch; ++u) {
+          const int32_t j = j0 + u * T;
+          if (j < used) in[j] = pr[u];
         }
-        in[j] = pr;
       }
     }
     // ---- sources with a view: mapped ends, zero-length mapped runs dropped ---------------

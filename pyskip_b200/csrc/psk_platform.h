@@ -31,6 +31,23 @@ namespace psk {
 PSK_HD int imin(int a, int b) { return a < b ? a : b; }
 PSK_HD int imax(int a, int b) { return a > b ? a : b; }
 
+// read-only global loads (ld.global.nc): never alias shared-memory stores, so the compiler
+// may hoist them above the staging stores
+PSK_D int32_t ld_nc(const int32_t* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+PSK_D uint32_t ld_nc(const uint32_t* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
 // volatile / relaxed accessors used by the decoupled look-back chain
 PSK_D unsigned long long ld_volatile_u64(const unsigned long long* p) {
   return *reinterpret_cast<const volatile unsigned long long*>(p);
