@@ -32,7 +32,7 @@
 namespace psk {
 
 #ifndef PSK_TILE_THREADS
-#define PSK_TILE_THREADS 256
+#define PSK_TILE_THREADS 512
 #endif
 #ifndef PSK_TILE_CAP
 #define PSK_TILE_CAP 6144
@@ -203,20 +203,23 @@ PSK_D int32_t block_exclusive_scan(int32_t v, int32_t* s_warp /*[T/32+1]*/, int3
 // Look-back chain word: (status << 32) | count.
 enum { ST_INVALID = 0, ST_AGGREGATE = 1, ST_PREFIX = 2 };
 
-// Decoupled look-back, executed by one full warp: lane l inspects tile (j - l); the nearest
-// tile that already published an inclusive PREFIX ends the walk, the AGGREGATEs in front of
-// it are summed.  Tiles are handed out by an atomic ticket, so every predecessor is resident
-// or finished and the spin cannot deadlock.
-PSK_D int32_t lookback_exclusive_warp(unsigned long long* state, int32_t tile, int32_t count) {
-  const int lane = threadIdx.x & 31;
+// Decoupled look-back, executed by the whole CTA: thread r inspects tile (j - r), so one
+// round covers T predecessors -- the persistent CTAs move through the tiles in lock step, and
+// a tile typically has to sum the AGGREGATEs of every tile of its own wave.  The nearest tile
+// that already published an inclusive PREFIX ends the walk.  Tiles are handed out by an
+// atomic ticket, so every predecessor is resident or finished and the spin cannot deadlock.
+template <int T>
+PSK_D int32_t lookback_exclusive_cta(unsigned long long* state, int32_t tile, int32_t count,
+                                     int32_t* s_sum /*[T/32]*/, int32_t* s_has /*[T/32]*/) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tile == 0) {
-    if (lane == 0) st_volatile_u64(&state[0], ((unsigned long long)ST_PREFIX << 32) | (uint32_t)count);
+    if (tid == 0) st_volatile_u64(&state[0], ((unsigned long long)ST_PREFIX << 32) | (uint32_t)count);
     return 0;
   }
-  if (lane == 0) st_volatile_u64(&state[tile], ((unsigned long long)ST_AGGREGATE << 32) | (uint32_t)count);
+  if (tid == 0) st_volatile_u64(&state[tile], ((unsigned long long)ST_AGGREGATE << 32) | (uint32_t)count);
   int32_t excl = 0;
-  for (int32_t j = tile - 1;; j -= 32) {
-    const int32_t idx = j - lane;
+  for (int32_t j = tile - 1;; j -= T) {
+    const int32_t idx = j - tid;
     unsigned long long w = (unsigned long long)ST_PREFIX << 32;  // virtual prefix 0 before tile 0
     if (idx >= 0) {
       do {
@@ -228,10 +231,23 @@ PSK_D int32_t lookback_exclusive_warp(unsigned long long* state, int32_t tile, i
     int32_t c = (lane <= first) ? (int32_t)(uint32_t)w : 0;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    excl += c;
-    if (pmask) break;
+    if (lane == 0) {
+      s_sum[warp] = c;
+      s_has[warp] = pmask != 0;
+    }
+    __syncthreads();
+    bool done = false;
+    for (int q = 0; q < T / 32; ++q) {  // every thread folds the warp results in tile order
+      excl += s_sum[q];
+      if (s_has[q]) {
+        done = true;
+        break;
+      }
+    }
+    __syncthreads();
+    if (done) break;
   }
-  if (lane == 0)
+  if (tid == 0)
     st_volatile_u64(&state[tile], ((unsigned long long)ST_PREFIX << 32) | (uint32_t)(excl + count));
   return excl;
 }
@@ -301,7 +317,8 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
   __shared__ int32_t s_off[PSK_MAX_SOURCES + 1];  // start of each source's slice in in[]
   __shared__ int32_t s_len[PSK_MAX_SOURCES];      // staged runs of each source (excl. look-ahead)
   __shared__ int32_t s_warp[T / 32 + 2];
-  __shared__ int32_t s_gofs, s_carry, s_fail, s_flat_total;
+  __shared__ int32_t s_lbhas[T / 32];
+  __shared__ int32_t s_carry, s_fail, s_flat_total;
 
   const int tid = threadIdx.x;
   const int k = p->k;
@@ -364,12 +381,18 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
           if (j < used) {
             // which source owns flat slot j: last i with s_off[i] <= j (view sources have
             // zero slots here and are never the last such i)
-            int l = 0, h = k - 1;
-            while (l < h) {
-              int mid = (l + h + 1) >> 1;
-              if (s_off[mid] <= j) l = mid; else h = mid - 1;
+            int i = 0;
+            if (K <= 8) {
+#pragma unroll
+              for (int q = 1; q < K; ++q) i += (q < k && s_off[q] <= j) ? 1 : 0;
+            } else {
+              int l = 0, h = k - 1;
+              while (l < h) {
+                int mid = (l + h + 1) >> 1;
+                if (s_off[mid] <= j) l = mid; else h = mid - 1;
+              }
+              i = l;
             }
-            const int i = l;
             const int32_t r = j - s_off[i];
             const int32_t idx = d.b0[i] + r;
             if (r < s_len[i] || idx < s_src[i].e) {
@@ -533,19 +556,13 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
     int32_t tile_total;
     const int32_t my_ofs = block_exclusive_scan<T>(n, s_warp, &tile_total);
     PSK_PHASE(4);  // waiting for the slowest thread + scan
-    if (tid < 32) {
-      const int32_t excl = lookback_exclusive_warp(p->tile_state, tile, tile_total);
-      if (tid == 0) {
-        s_gofs = excl;
-        if (tile == n_tiles - 1) p->ctrl[CTRL_COUNT] = excl + tile_total;
-      }
-    }
     // in[] is dead (every thread passed the scan's barriers): reuse it as the compacted
     // staging area so that the global write is fully coalesced
     for (int32_t j = 0; j < n; ++j) in[my_ofs + j] = out[base + j];
+    const int32_t gofs = lookback_exclusive_cta<T>(p->tile_state, tile, tile_total, s_warp, s_lbhas);
+    if (tid == 0 && tile == n_tiles - 1) p->ctrl[CTRL_COUNT] = gofs + tile_total;
     __syncthreads();
     PSK_PHASE(5);  // look-back + smem compaction
-    const int32_t gofs = s_gofs;
     if (gofs + tile_total <= p->out_capacity) {
       for (int32_t j = tid; j < tile_total; j += T) {
         const int2 r = in[j];
