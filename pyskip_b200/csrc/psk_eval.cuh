@@ -46,13 +46,19 @@ constexpr int kSentinel = 0x7fffffff;
 // the product library.
 #ifdef PSK_PHASE_TIMING
 #define PSK_PHASE_DECL long long ph_t = clock64(); long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
-#define PSK_PHASE(i)                                   \
-  do {                                                 \
-    if (threadIdx.x == 0) {                            \
-      long long now_ = clock64();                      \
-      ph_acc[i] += now_ - ph_t;                        \
-      ph_t = now_;                                     \
-    }                                                  \
+#define PSK_PHASE(i)                                                              \
+  do {                                                                            \
+    if (threadIdx.x == 0) {                                                       \
+      long long now_ = clock64();                                                 \
+      ph_acc[i] += now_ - ph_t;                                                   \
+      ph_t = now_;                                                                \
+      if (p->trace) {                                                             \
+        unsigned long long gt_;                                                   \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                   \
+        p->trace[(long long)tile * 8 + (i)] = gt_;                                \
+        if ((i) == 0) p->trace[(long long)tile * 8 + 7] = blockIdx.x;             \
+      }                                                                           \
+    }                                                                             \
   } while (0)
 #define PSK_PHASE_FLUSH                                                                      \
   do {                                                                                       \
@@ -303,18 +309,22 @@ PSK_D void fetch_tile_desc(DPlan* p, TileDesc* d, int k, int32_t n_tiles) {
   }
 }
 
-template <int K, typename Eval>
-PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& ev) {
+// TYPED_FLOAT: compaction compares float values with operator== (PSK_EQ_TYPED on F32)
+// instead of the 32-bit payloads.
+template <int K, bool TYPED_FLOAT, typename Eval>
+PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
   constexpr int T = kTileThreads;
   constexpr int CAP = kTileCap;
   constexpr int IN_N = CAP + PSK_MAX_SOURCES;  // room for one look-ahead run per source
 
-  int2* in = reinterpret_cast<int2*>(smem_raw);
-  int2* out = in + IN_N;
+  // one dynamic shared array, indexed directly (no derived pointers: keeps every access a
+  // plain LDS/STS off the static shared base): [0, IN_N) = in, [IN_N, IN_N + CAP) = out
+  PSK_DYN_SMEM(smem_raw);
+  const SmemPairs sm(smem_raw);
 
   __shared__ TileDesc s_desc[2];
   __shared__ SrcDesc s_src[PSK_MAX_SOURCES];
-  __shared__ int32_t s_off[PSK_MAX_SOURCES + 1];  // start of each source's slice in in[]
+  __shared__ int32_t s_off[PSK_MAX_SOURCES + 1];  // start of each source's slice in the tile buffer
   __shared__ int32_t s_len[PSK_MAX_SOURCES];      // staged runs of each source (excl. look-ahead)
   __shared__ int32_t s_warp[T / 32 + 2];
   __shared__ int32_t s_lbhas[T / 32];
@@ -322,7 +332,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
 
   const int tid = threadIdx.x;
   const int k = p->k;
-  const bool typed_float = p->eq != 0;
+  constexpr bool typed_float = TYPED_FLOAT;
   const bool any_views = p->any_views != 0;
   const int32_t span = p->span;
   const int32_t n_tiles = p->n_tiles;
@@ -334,6 +344,11 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
     s_src[tid].nviews = s.nviews;
     s_src[tid].e = s.e;
   }
+  // Persistent CTAs that start together stay in lock step (same phase at the same time: HBM
+  // bursts, then idles, and every tile waits in the look-back for its whole wave).  A start
+  // delay proportional to the CTA index spreads them over one tile period; from then on a
+  // tile's predecessors were started earlier and have published by the time it looks back.
+  if (p->stagger_ns > 0 && blockIdx.x > 0) sleep_ns((unsigned)(p->stagger_ns * (int)blockIdx.x));
   if (tid < 32) fetch_tile_desc(p, &s_desc[0], k, n_tiles);
   __syncthreads();
 
@@ -404,7 +419,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
 #pragma unroll
         for (int u = 0; u < kStageBatch; ++u) {
           const int32_t j = j0 + u * T;
-          if (j < used) in[j] = pr[u];
+          if (j < used) sm.st(j, pr[u].x, pr[u].y);
         }
       }
     }
@@ -432,7 +447,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
           __syncthreads();  // s_last consumed before the scan reuses s_warp
           int32_t tot;
           const int32_t pos = block_exclusive_scan<T>(keep ? 1 : 0, s_warp, &tot);
-          if (keep && off + kept + pos < IN_N) in[off + kept + pos] = make_int2(me, (int32_t)s.vals[idx]);
+          if (keep && off + kept + pos < IN_N) sm.st(off + kept + pos, me, (int32_t)s.vals[idx]);
           kept += tot;
           const int32_t last_valid = (b1 - base < T ? b1 - base : T) - 1;
           if (tid == last_valid) s_carry = me;
@@ -442,7 +457,8 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
           break;
         }
         if (tid == 0) {
-          in[off + kept] = (b1 < s.e) ? make_int2(mapped_end(s, b1), (int32_t)s.vals[b1]) : make_int2(kSentinel, 0);
+          if (b1 < s.e) sm.st(off + kept, mapped_end(s, b1), (int32_t)s.vals[b1]);
+          else sm.st(off + kept, kSentinel, 0);
           s_off[i] = off;
           s_len[i] = kept;
         }
@@ -477,7 +493,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
         for (int i = 0; i < K; ++i) {
           const int32_t half = rem[i] >> 1;
           if (half > 0) {
-            const bool right = in[cur[i] + half - 1].x <= c0;
+            const bool right = sm.ldx(cur[i] + half - 1) <= c0;
             cur[i] += right ? half : 0;
             rem[i] -= half;
           }
@@ -487,7 +503,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
 #pragma unroll
     for (int i = 0; i < K; ++i) {
       if (i < k && !fail) {
-        const int2 pr = in[cur[i]];
+        const int2 pr = sm.ld(cur[i]);
         head[i] = pr.x;
         val[i] = (uint32_t)pr.y;
         base += cur[i] - s_off[i];
@@ -513,7 +529,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
       if (e != last_e) {
         const uint32_t v = ev(val);  // value of the span that ends at e
         if (have && !payload_equal(pv, v, typed_float)) {
-          out[base + n] = make_int2(pe, (int32_t)pv);
+          sm.st(IN_N + base + n, pe, (int32_t)pv);
           ++n;
         }
         pe = e;
@@ -530,7 +546,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
           idx = cur[i];
         }
       }
-      const int2 nx = in[idx + 1];
+      const int2 nx = sm.ld(idx + 1);
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         if (i == j) {
@@ -546,7 +562,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
       bool keep = (pe == span);
       if (!keep) keep = !payload_equal(pv, ev(val), typed_float);
       if (keep) {
-        out[base + n] = make_int2(pe, (int32_t)pv);
+        sm.st(IN_N + base + n, pe, (int32_t)pv);
         ++n;
       }
     }
@@ -556,16 +572,19 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
     int32_t tile_total;
     const int32_t my_ofs = block_exclusive_scan<T>(n, s_warp, &tile_total);
     PSK_PHASE(4);  // waiting for the slowest thread + scan
-    // in[] is dead (every thread passed the scan's barriers): reuse it as the compacted
+    // the input half of the tile buffer is dead (every thread passed the scan's barriers): reuse it as the compacted
     // staging area so that the global write is fully coalesced
-    for (int32_t j = 0; j < n; ++j) in[my_ofs + j] = out[base + j];
+    for (int32_t j = 0; j < n; ++j) {
+      const int2 r = sm.ld(IN_N + base + j);
+      sm.st(my_ofs + j, r.x, r.y);
+    }
     const int32_t gofs = lookback_exclusive_cta<T>(p->tile_state, tile, tile_total, s_warp, s_lbhas);
     if (tid == 0 && tile == n_tiles - 1) p->ctrl[CTRL_COUNT] = gofs + tile_total;
     __syncthreads();
     PSK_PHASE(5);  // look-back + smem compaction
     if (gofs + tile_total <= p->out_capacity) {
       for (int32_t j = tid; j < tile_total; j += T) {
-        const int2 r = in[j];
+        const int2 r = sm.ld(j);
         p->out_ends[gofs + j] = r.x;
         p->out_vals[gofs + j] = (uint32_t)r.y;
       }
@@ -580,12 +599,12 @@ PSK_D void merge_eval_tile_loop(DPlan* p, unsigned char* smem_raw, const Eval& e
 
 template <int K>
 __global__ void __launch_bounds__(kTileThreads) k_merge_eval_interp(DPlan* p) {
-  PSK_DYN_SMEM(smem_raw);
   __shared__ psk_node s_prog[PSK_MAX_PROGRAM];
   for (int i = threadIdx.x; i < p->nprog; i += blockDim.x) s_prog[i] = p->prog[i];
   __syncthreads();
   InterpEval ev{s_prog, p->nprog};
-  merge_eval_tile_loop<K>(p, smem_raw, ev);
+  if (p->eq != 0) merge_eval_tile_loop<K, true>(p, ev);
+  else merge_eval_tile_loop<K, false>(p, ev);
 }
 
 constexpr unsigned kMergeEvalSmemBytes = ((kTileCap + PSK_MAX_SOURCES) + kTileCap) * 8;

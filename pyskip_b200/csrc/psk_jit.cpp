@@ -125,7 +125,7 @@ bool load_api() {
 
 // postfix program -> straight-line SSA over apply_unary / apply_binary with literal op-codes
 // (the switch inside them folds away at compile time)
-std::string gen_source(int K, int nprog, const psk_node* prog) {
+std::string gen_source(int K, bool typed_float, int nprog, const psk_node* prog) {
   std::string body;
   std::vector<int> st;
   int next = 0;
@@ -136,7 +136,7 @@ std::string gen_source(int K, int nprog, const psk_node* prog) {
       snprintf(buf, sizeof buf, "    const uint32_t t%d = v[%u];\n", next, prog[i].arg);
       st.push_back(next++);
     } else if (op == PSK_OP_CONST) {
-      snprintf(buf, sizeof buf, "    const uint32_t t%d = cst[%d];\n", next, i);
+      snprintf(buf, sizeof buf, "    const uint32_t t%d = c%d;\n", next, i);
       st.push_back(next++);
     } else if (op == PSK_OP_SELECT) {
       int c = st.back(); st.pop_back();
@@ -159,28 +159,35 @@ std::string gen_source(int K, int nprog, const psk_node* prog) {
   snprintf(buf, sizeof buf, "    return t%d;\n", st.back());
   body += buf;
 
-  std::string src = "#include \"psk_eval.cuh\"\nnamespace psk {\nstruct JitEval {\n  const uint32_t* cst;\n"
+  // immediates are run-time data (one module serves every set of constants): loaded from
+  // the plan into registers once per thread
+  std::string members, inits;
+  for (int i = 0; i < nprog; ++i) {
+    if (prog[i].op != PSK_OP_CONST) continue;
+    snprintf(buf, sizeof buf, "  uint32_t c%d;\n", i);
+    members += buf;
+    snprintf(buf, sizeof buf, "  ev.c%d = p->prog[%d].arg;\n", i, i);
+    inits += buf;
+  }
+  std::string src = "#include \"psk_eval.cuh\"\nnamespace psk {\nstruct JitEval {\n" + members +
                     "  template <typename ValArray>\n"
                     "  __device__ __forceinline__ uint32_t operator()(const ValArray& v) const {\n";
   src += body;
   src += "  }\n};\n}  // namespace psk\n";
   snprintf(buf, sizeof buf,
-           "extern \"C\" __global__ void __launch_bounds__(psk::kTileThreads) psk_jit_merge_eval(psk::DPlan* p) {\n"
-           "  extern __shared__ __align__(16) unsigned char smem_raw[];\n"
-           "  __shared__ uint32_t s_cst[%d];\n"
-           "  for (int i = threadIdx.x; i < %d; i += blockDim.x) s_cst[i] = p->prog[i].arg;\n"
-           "  __syncthreads();\n"
-           "  psk::JitEval ev{s_cst};\n"
-           "  psk::merge_eval_tile_loop<%d>(p, smem_raw, ev);\n}\n",
-           nprog, nprog, K);
+           "  psk::merge_eval_tile_loop<%d, %s>(p, ev);\n}\n", K, typed_float ? "true" : "false");
+  src += "extern \"C\" __global__ void __launch_bounds__(psk::kTileThreads) psk_jit_merge_eval(psk::DPlan* p) {\n"
+         "  psk::JitEval ev;\n";
+  src += inits;
   src += buf;
   return src;
 }
 
-std::string cache_key(int K, int nprog, const psk_node* prog) {
+std::string cache_key(int K, bool typed_float, int nprog, const psk_node* prog) {
   std::string key;
   key.reserve(nprog * 3 + 8);
   key += (char)K;
+  key += typed_float ? 'T' : 'B';
   for (int i = 0; i < nprog; ++i) {
     key += (char)prog[i].op;
     key += (char)(prog[i].op == PSK_OP_SRC ? prog[i].arg : 0);
@@ -188,8 +195,9 @@ std::string cache_key(int K, int nprog, const psk_node* prog) {
   return key;
 }
 
-bool compile_cubin(int K, int nprog, const psk_node* prog, std::vector<char>* cubin, std::string* why) {
-  const std::string src = gen_source(K, nprog, prog);
+bool compile_cubin(int K, bool typed_float, int nprog, const psk_node* prog, std::vector<char>* cubin,
+                   std::string* why) {
+  const std::string src = gen_source(K, typed_float, nprog, prog);
   nvrtcProgram np = nullptr;
   int r = g_api.nvrtcCreateProgram(&np, src.c_str(), "psk_jit_merge_eval.cu", kJitNumHeaders, kJitHeaderSources,
                                    kJitHeaderNames);
@@ -238,9 +246,9 @@ bool compile_cubin(int K, int nprog, const psk_node* prog, std::vector<char>* cu
   return true;
 }
 
-JitKernel* compile(int K, int nprog, const psk_node* prog, std::string* why) {
+JitKernel* compile(int K, bool typed_float, int nprog, const psk_node* prog, std::string* why) {
   std::vector<char> cubin;
-  if (!compile_cubin(K, nprog, prog, &cubin, why)) return nullptr;
+  if (!compile_cubin(K, typed_float, nprog, prog, &cubin, why)) return nullptr;
   void* mod = nullptr;
   int r = g_api.cuModuleLoadData(&mod, cubin.data());
   if (r != 0) {
@@ -260,20 +268,20 @@ JitKernel* compile(int K, int nprog, const psk_node* prog, std::string* why) {
 
 }  // namespace
 
-const JitKernel* jit_get_merge_eval(int K, int nprog, const psk_node* prog, const char** why) {
+const JitKernel* jit_get_merge_eval(int K, bool typed_float, int nprog, const psk_node* prog, const char** why) {
   std::lock_guard<std::mutex> l(g_mu);
   static std::string s_why;
   if (!load_api()) {
     if (why) *why = g_api.why.c_str();
     return nullptr;
   }
-  const std::string key = cache_key(K, nprog, prog);
+  const std::string key = cache_key(K, typed_float, nprog, prog);
   auto it = g_cache.find(key);
   if (it != g_cache.end()) {
     if (!it->second && why) *why = "previous compilation of this program failed";
     return it->second;
   }
-  JitKernel* k = compile(K, nprog, prog, &s_why);
+  JitKernel* k = compile(K, typed_float, nprog, prog, &s_why);
   if (k) {
     ++g_compiled;
   } else {
@@ -300,11 +308,11 @@ int jit_launch(const JitKernel* k, unsigned grid, unsigned block, size_t smem, v
   return g_api.cuLaunchKernel(k->function, grid, 1, 1, block, 1, 1, (unsigned)smem, stream, args, nullptr);
 }
 
-int jit_compile_check(int K, int nprog, const psk_node* prog, char* log, int loglen) {
+int jit_compile_check(int K, bool typed_float, int nprog, const psk_node* prog, char* log, int loglen) {
   std::lock_guard<std::mutex> l(g_mu);
   std::string why;
   std::vector<char> cubin;
-  bool ok = load_nvrtc() && compile_cubin(K, nprog, prog, &cubin, &why);
+  bool ok = load_nvrtc() && compile_cubin(K, typed_float, nprog, prog, &cubin, &why);
   if (!ok && why.empty()) why = g_api.why;
   if (log && loglen > 0) {
     std::string msg = ok ? ("ok cubin bytes=" + std::to_string(cubin.size())) : why;

@@ -51,7 +51,7 @@ struct DPlan {
   int32_t max_tiles;
   int32_t out_capacity;
   int32_t any_views;
-  int32_t pad0;
+  int32_t stagger_ns;  // start delay per CTA index: de-phases the persistent CTAs
   // scratch + output (device pointers)
   int32_t* merged;                 // [max_samples] sorted sample keys
   int32_t* bounds;                 // [(max_tiles+1) * k] per-tile raw index bounds
@@ -59,6 +59,7 @@ struct DPlan {
   unsigned long long* tile_state;  // [max_tiles] look-back chain
   int32_t* ctrl;                   // [0]=ticket [1]=out_count [2]=error
   unsigned long long* phase;       // [8] cycle counters (PSK_PHASE_TIMING builds only)
+  unsigned long long* trace;       // [max_tiles * 8] per-tile globaltimer stamps (same builds)
   int32_t* out_ends;
   uint32_t* out_vals;
   psk_node prog[PSK_MAX_PROGRAM];

@@ -13,6 +13,7 @@
 #define PSK_LAUNCH(kernel, grid, block, smem, stream, ...) \
   psk_sim::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
 #define PSK_DYN_SMEM(name) unsigned char* name = psk_sim::dyn_smem()
+#define PSK_DYN_SMEM_PAIRS(name) int2* name = reinterpret_cast<int2*>(psk_sim::dyn_smem())
 #define PSK_HD inline
 #define PSK_D inline
 #else
@@ -22,6 +23,7 @@
 #define PSK_LAUNCH(kernel, grid, block, smem, stream, ...) \
   kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define PSK_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define PSK_DYN_SMEM_PAIRS(name) extern __shared__ __align__(16) int2 name[]
 #define PSK_HD __host__ __device__ __forceinline__
 #define PSK_D __device__ __forceinline__
 #endif
@@ -45,6 +47,50 @@ PSK_D uint32_t ld_nc(const uint32_t* p) {
   return __ldg(p);
 #else
   return *p;
+#endif
+}
+
+// The tile buffer in dynamic shared memory, addressed by 32-bit shared-window offsets with
+// explicit ld.shared / st.shared: nvcc otherwise re-derives the generic address of dynamic
+// shared memory (S2R SR_CgaCtaId + LEA) inside the merge loop.
+struct SmemPairs {
+#if defined(__CUDA_ARCH__)
+  uint32_t base;
+  PSK_D explicit SmemPairs(void* p) {
+    // volatile: computed once and kept in a register (never rematerialised in the loops)
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(base) : "l"(p));
+  }
+  PSK_D int2 ld(int i) const {
+    int2 r;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(base + (uint32_t)i * 8u));
+    return r;
+  }
+  PSK_D int ldx(int i) const {
+    int r;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(base + (uint32_t)i * 8u));
+    return r;
+  }
+  PSK_D void st(int i, int x, int y) const {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base + (uint32_t)i * 8u), "r"(x), "r"(y) : "memory");
+  }
+#else
+  int2* ptr;
+  explicit SmemPairs(void* p) : ptr(reinterpret_cast<int2*>(p)) {}
+  int2 ld(int i) const { return ptr[i]; }
+  int ldx(int i) const { return ptr[i].x; }
+  void st(int i, int x, int y) const { ptr[i] = make_int2(x, y); }
+#endif
+};
+
+PSK_D void sleep_ns(unsigned ns) {
+#if defined(__CUDA_ARCH__)
+  while (ns > 0) {  // __nanosleep takes at most ~1 ms
+    unsigned step = ns > 500000u ? 500000u : ns;
+    __nanosleep(step);
+    ns -= step;
+  }
+#else
+  (void)ns;
 #endif
 }
 

@@ -52,6 +52,9 @@ struct Ctx {
   unsigned long long phase_cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int64_t jit_min_runs = 1 << 18;  // evaluations at least this large get a specialised kernel
   int64_t jit_launches = 0;
+  int stagger_ns = 0;
+  unsigned long long* trace_buf = nullptr;  // PSK_PHASE_TIMING builds: device trace buffer
+  int64_t trace_cap = 0, trace_tiles = 0;
   DPlan* h_plan = nullptr;      // pinned staging copy of the plan
   int32_t* h_ctrl = nullptr;    // pinned read-back of CTRL words / small results
   std::atomic<int64_t> launches{0};
@@ -125,6 +128,7 @@ psk_status do_init(int device) {
   CUDA_TRY(cudaFuncSetAttribute(k_merge_eval_interp<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CUDA_TRY(cudaFuncSetAttribute(k_merge_eval_interp<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CUDA_TRY(cudaFuncSetAttribute(k_merge_eval_interp<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  if (const char* sv = getenv("PSKB200_STAGGER_NS")) g.stagger_ns = atoi(sv);
   g.device = device;
   g.inited = true;
   return PSK_OK;
@@ -403,7 +407,7 @@ int32_t psk_jit_compile_check(int32_t k, int32_t nprog, const psk_node* prog, ch
   return -1;
 #else
   if (validate_program(k, nprog, prog) != PSK_OK) return 2;
-  return jit_compile_check(pick_K(k), nprog, prog, log, loglen);
+  return jit_compile_check(k, false, nprog, prog, log, loglen);
 #endif
 }
 
@@ -416,6 +420,22 @@ psk_status psk_profile(int32_t enable) {
 }
 
 #ifdef PSK_PHASE_TIMING
+// development builds only: per-tile globaltimer trace of the next evaluations
+PSK_API int32_t psk_trace_enable(int64_t max_tiles) {
+  if (ensure_init() != PSK_OK) return 1;
+  if (g.trace_buf) cudaFree(g.trace_buf);
+  g.trace_cap = max_tiles * 8;
+  if (cudaMalloc(reinterpret_cast<void**>(&g.trace_buf), (size_t)g.trace_cap * 8) != cudaSuccess) return 2;
+  cudaMemset(g.trace_buf, 0, (size_t)g.trace_cap * 8);
+  return 0;
+}
+PSK_API int64_t psk_trace_read(unsigned long long* out, int64_t cap_words) {
+  cudaStreamSynchronize(g.stream);
+  int64_t n = g.trace_tiles * 8;
+  if (n > cap_words) n = cap_words;
+  cudaMemcpy(out, g.trace_buf, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  return g.trace_tiles;
+}
 // development builds only (tools/phase_profile.py); not part of include/pskb200.h
 PSK_API void psk_phase_read(unsigned long long* out8, int32_t reset) {
   for (int q = 0; q < 8; ++q) {
@@ -702,6 +722,7 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
   PSK_CHECK_ARG(total_runs < 0x7ffffff0LL);
   hp.span = (int32_t)span;
   hp.any_views = any_views ? 1 : 0;
+  hp.stagger_ns = g.stagger_ns;
 
   // ---- partition parameters: S * (m + 2k) <= kTileCap bounds the runs of one tile --------
   int S = k <= 4 ? 256 : k <= 8 ? 128 : k <= 16 ? 64 : 32;
@@ -755,6 +776,13 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
   hp.tile_state = reinterpret_cast<unsigned long long*>(scratch + o_state);
   hp.ctrl = reinterpret_cast<int32_t*>(scratch + o_ctrl);
   hp.phase = reinterpret_cast<unsigned long long*>(scratch + o_phase);
+  hp.trace = nullptr;
+#ifdef PSK_PHASE_TIMING
+  if (g.trace_buf && max_tiles * 8 <= g.trace_cap) {
+    hp.trace = g.trace_buf;
+    g.trace_tiles = max_tiles;
+  }
+#endif
   hp.merged = reinterpret_cast<int32_t*>(scratch + o_merged);
   hp.bounds = reinterpret_cast<int32_t*>(scratch + o_bounds);
   hp.tile_hi = reinterpret_cast<int32_t*>(scratch + o_hi);
@@ -780,7 +808,8 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
 #ifndef PSK_CPU_SIM
     if (total_runs >= g.jit_min_runs) {
       // the same kernel template with the program compiled in (psk_jit.h)
-      if (const JitKernel* jk = jit_get_merge_eval(pick_K(k), nprog, prog, nullptr)) {
+      // K = k exactly: no padding sources in the specialised kernel
+      if (const JitKernel* jk = jit_get_merge_eval(k, hp.eq != 0, nprog, prog, nullptr)) {
         if (jit_launch(jk, (unsigned)grid, kTileThreads, kMergeEvalSmemBytes, g.stream, d_plan) == 0) {
           launched = true;
           g.launches.fetch_add(1, std::memory_order_relaxed);

@@ -54,6 +54,23 @@ if not args.no_phase:
     lib.c.psk_phase_read(buf, 1)
 ms, ne, ri, ro = lib.profile_read()
 tot = sum(buf)
+if not args.no_phase:
+    # one traced evaluation: per-tile globaltimer stamps at the end of each phase
+    lib.c.psk_trace_enable.argtypes = [C.c_int64]
+    lib.c.psk_trace_read.restype = C.c_int64
+    lib.c.psk_trace_read.argtypes = [C.c_void_p, C.c_int64]
+    if lib.c.psk_trace_enable(20000) == 0:
+        lib.eval(srcs, prog, A.F32)
+        tr = np.zeros(20000 * 8, dtype=np.uint64)
+        nt = lib.c.psk_trace_read(tr.ctypes.data_as(C.c_void_p), tr.size)
+        tr = tr[:nt * 8].reshape(-1, 8)
+        tr = tr[tr[:, 0] > 0]
+        np.save(os.path.join(ROOT, "gpurun_out", f"trace_{args.threads}_{args.cap}.npy"), tr)
+        t0 = tr[:, :7].astype(np.int64)
+        d = np.diff(t0, axis=1)
+        print("per-tile phase durations (ns) median / p90:",
+              [(int(np.median(d[:, i])), int(np.percentile(d[:, i], 90))) for i in range(6)])
+        print("tile start spread: first", int(t0[:, 0].min() - t0[:, 0].min()), "last", int(t0[:, 6].max() - t0[:, 0].min()))
 names = ["ticket+desc", "staging", "thread search", "merge (thread 0)", "wait slowest+scan", "lookback+compact",
          "global write", "-"]
 print(f"threads {args.threads or 256} cap {args.cap or 6144}")
