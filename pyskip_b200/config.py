@@ -1,0 +1,64 @@
+"""Configuration scopes (src/pyskip/config.py:8-58) over the extension's global config map.
+
+Keys understood by the GPU backend: ``flush_tree_size_threshold`` (expression size above
+which an array is evaluated eagerly; reference array.hpp:210).  ``accelerated_eval``,
+``parallelize_threshold`` and ``parallelize_parts`` are accepted for compatibility and have
+no effect (they select CPU code paths; results never depended on them)."""
+from contextlib import contextmanager
+
+from . import _pyskip_b200_ext as _ext
+from .exceptions import TypeConversionError
+
+_cfg = _ext.config
+
+
+def get_all_values():
+    return _cfg.get_all_values()
+
+
+def set_value(name, val):
+    if isinstance(val, bool):
+        _cfg.set_bool_value(name, val)
+    elif isinstance(val, int):
+        _cfg.set_int_value(name, val)
+    elif isinstance(val, float):
+        _cfg.set_float_value(name, val)
+    elif isinstance(val, str):
+        _cfg.set_string_value(name, val)
+    else:
+        raise TypeConversionError(f"Unsupported type for config map: {type(val)}")
+
+
+@contextmanager
+def config_scope(**kwargs):
+    saved = _cfg.get_all_values()
+    try:
+        for key, val in kwargs.items():
+            set_value(key, val)
+        yield
+    finally:
+        _cfg.set_all_values(saved)
+
+
+@contextmanager
+def num_threads_scope(num):
+    with config_scope(parallelize_parts=int(num)):
+        yield
+
+
+@contextmanager
+def flush_threshold_scope(num):
+    with config_scope(flush_tree_size_threshold=int(num)):
+        yield
+
+
+@contextmanager
+def lazy_evaluation_scope():
+    with flush_threshold_scope(2 ** 30):
+        yield
+
+
+@contextmanager
+def greedy_evaluation_scope():
+    with flush_threshold_scope(0):
+        yield

@@ -730,7 +730,9 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
   int64_t max_samples = 0;
   for (int i = 0; i < k; ++i) max_samples += (hp.src[i].nruns + S - 1) / S;
   const int m_max = kTileCap / S - 2 * k;
-  int m = (int)(max_samples / (2 * (int64_t)g.sm_count));
+  int m = (int)(max_samples / (2 * (int64_t)g.sm_count));  // aim at >= 2 tiles per SM ...
+  const int m_small = 2048 / S;                            // ... but not at tiles below ~2k runs
+  if (m < m_small) m = m_small;
   if (m > m_max) m = m_max;
   if (m < 1) m = 1;
   const int64_t max_tiles = (max_samples + m - 1) / m + 1;

@@ -27,3 +27,19 @@ def lib(request):
 def scale(lib):
     """Problem-size multiplier: the simulator runs one OS thread per CUDA thread."""
     return 1 if lib.is_simulator() else 40
+
+
+@pytest.fixture(params=["sim", pytest.param("cuda", marks=pytest.mark.gpu)])
+def api(request):
+    """(pyskip_b200 package, extension module) bound to the simulator or the CUDA library.
+    The extension has one process-wide backend, so the fixture re-binds it per test."""
+    import helpers
+    import pyskip_b200 as ps
+    from pyskip_b200 import _abi, _pyskip_b200_ext as E
+    if request.param == "sim":
+        E._bind_backend(helpers.build_sim(), True)
+        assert E._backend_is_simulator() == 1
+    else:
+        E._bind_backend(_abi._LIB_PATH, True)
+        assert E._backend_is_simulator() == 0
+    return ps, E

@@ -31,7 +31,7 @@ def build_sim():
     if os.path.exists(SIM_LIB) and all(os.path.getmtime(SIM_LIB) >= os.path.getmtime(s) for s in srcs):
         return SIM_LIB
     os.makedirs(os.path.dirname(SIM_LIB), exist_ok=True)
-    cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-DPSK_CPU_SIM", "-ffp-contract=off",
+    cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-DPSK_CPU_SIM", "-DPSK_TILE_THREADS=128", "-ffp-contract=off",
            "-Wno-unknown-pragmas", "-x", "c++", os.path.join(ROOT, "pyskip_b200", "csrc", "pskb200_abi.cu"),
            "-x", "c++", os.path.join(SIM_DIR, "cuda_sim.cpp"), "-I" + SIM_DIR,
            "-I" + os.path.join(ROOT, "pyskip_b200", "csrc"), "-pthread", "-o", SIM_LIB]

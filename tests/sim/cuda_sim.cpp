@@ -1,6 +1,8 @@
 // cuda_sim.cpp -- TEST INFRASTRUCTURE ONLY (see cuda_sim.h).
 #include "cuda_sim.h"
 
+#include <semaphore>
+
 thread_local psk_sim_uint3 threadIdx;
 psk_sim_uint3 blockIdx, blockDim, gridDim;
 
@@ -11,82 +13,56 @@ unsigned char* g_dyn_smem = nullptr;
 
 namespace {
 
-// A persistent pool: worker i runs CUDA thread i of the current block.
+// A persistent pool: worker i runs CUDA thread i of the current block.  Each worker sleeps on
+// its own semaphore, so a 32-thread block wakes 32 workers, not the whole pool.
 class Pool {
  public:
-  ~Pool() {
-    {
-      std::lock_guard<std::mutex> l(mu_);
-      stop_ = true;
-      gen_++;
-    }
-    cv_.notify_all();
-    for (auto& t : th_) t.join();
-  }
-
   void run_block(unsigned nthreads, const std::function<void()>& fn) {
     grow(nthreads);
-    {
-      std::lock_guard<std::mutex> l(mu_);
-      fn_ = &fn;
-      active_ = nthreads;
-      done_ = 0;
-      gen_++;
-    }
-    cv_.notify_all();
+    fn_ = &fn;
+    remaining_.store((int)nthreads, std::memory_order_release);
+    for (unsigned i = 0; i < nthreads; ++i) workers_[i]->go.release();
     std::unique_lock<std::mutex> l(mu_);
-    cv_done_.wait(l, [&] { return done_ == th_.size(); });
+    cv_done_.wait(l, [&] { return remaining_.load(std::memory_order_acquire) == 0; });
   }
 
  private:
+  struct Worker {
+    std::binary_semaphore go{0};
+    std::thread th;
+  };
+
   void grow(unsigned n) {
-    while (th_.size() < n) {
-      unsigned id = (unsigned)th_.size();
-      uint64_t start_gen;
-      {
-        std::lock_guard<std::mutex> l(mu_);
-        start_gen = gen_;
-      }
-      th_.emplace_back([this, id, start_gen] { worker(id, start_gen); });
+    while (workers_.size() < n) {
+      unsigned id = (unsigned)workers_.size();
+      workers_.emplace_back(std::make_unique<Worker>());
+      Worker* w = workers_.back().get();
+      w->th = std::thread([this, id, w] { worker(id, w); });
+      w->th.detach();
     }
   }
 
-  void worker(unsigned id, uint64_t seen) {
+  void worker(unsigned id, Worker* w) {
     for (;;) {
-      const std::function<void()>* fn;
-      unsigned active;
-      {
-        std::unique_lock<std::mutex> l(mu_);
-        cv_.wait(l, [&] { return gen_ != seen; });
-        seen = gen_;
-        if (stop_) return;
-        fn = fn_;
-        active = active_;
-      }
-      if (id < active) {
-        threadIdx.x = id;
-        threadIdx.y = threadIdx.z = 0;
-        (*fn)();
-        // a CUDA thread that has exited no longer takes part in barriers
-        g_ctx->warp_bar[id >> 5]->arrive_and_drop();
-        g_ctx->block_bar->arrive_and_drop();
-      }
-      {
+      w->go.acquire();
+      threadIdx.x = id;
+      threadIdx.y = threadIdx.z = 0;
+      (*fn_)();
+      // a CUDA thread that has exited no longer takes part in barriers
+      g_ctx->warp_bar[id >> 5]->arrive_and_drop();
+      g_ctx->block_bar->arrive_and_drop();
+      if (remaining_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
         std::lock_guard<std::mutex> l(mu_);
-        done_++;
-        if (done_ == th_.size()) cv_done_.notify_all();
+        cv_done_.notify_all();
       }
     }
   }
 
-  std::vector<std::thread> th_;
+  std::vector<std::unique_ptr<Worker>> workers_;
   std::mutex mu_;
-  std::condition_variable cv_, cv_done_;
-  uint64_t gen_ = 0;
-  bool stop_ = false;
+  std::condition_variable cv_done_;
+  std::atomic<int> remaining_{0};
   const std::function<void()>* fn_ = nullptr;
-  unsigned active_ = 0;
-  size_t done_ = 0;
 };
 
 Pool& pool() {
