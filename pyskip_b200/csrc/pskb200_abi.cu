@@ -138,8 +138,12 @@ psk_status ensure_init() {
   if (g.inited) return PSK_OK;
   std::lock_guard<std::mutex> l(g.mu);
   if (g.inited) return PSK_OK;
-  const char* env = getenv("LOCAL_RANK");
+#ifdef PSK_CPU_SIM
+  return do_init(0);
+#else
+  const char* env = getenv("LOCAL_RANK");  // one process per GPU (torchrun)
   return do_init(env ? atoi(env) : 0);
+#endif
 }
 
 psk_status dmalloc(void** p, size_t bytes) {

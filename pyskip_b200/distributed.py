@@ -1,0 +1,252 @@
+"""Multi-GPU execution of the RLE path: one process per GPU (torch.distributed; NCCL over
+NVLink/NVSwitch on B200, gloo in the CPU tests), arrays sharded by COORDINATE RANGE.
+
+This is the GPU-box form of the reference's only parallel strategy, the coordinate-range
+partition of eval::partition_pool (include/pyskip/detail/eval.hpp:448-462) followed by
+eval::fuse_stores (:568-607):
+
+  * rank r of R owns output coordinates [r*span/R, (r+1)*span/R) (the same uint64 split as
+    eval.hpp:452-456) and holds its shard with LOCAL int32 coordinates plus an int64 global
+    offset, so spans beyond 2^31 (BASELINE configs 4 and 5) are representable;
+  * element-wise evaluation of co-partitioned operands needs no communication at all;
+  * stitching is one tiny all-gather of (first value, last value, run count) per rank: a
+    shard drops its last run when the next non-empty shard starts with an equal value
+    (eval.hpp:581-588) and an exclusive scan of the surviving counts gives global run offsets;
+  * reductions are a local one-pass reduction + one scalar all-reduce;
+  * the 3-D convolution partitions the slowest axis (z) into slabs and exchanges one boundary
+    z-slice per neighbour AS RUNS (ends + values), edge ranks use the fill value.
+
+The collectives move a few words (stitch, reductions) or the runs of a single z-slice
+(halo), so they are latency- not bandwidth-bound; there is no compute kernel whose tiles
+feed a collective, hence no fused compute+collective kernel on this path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _pyskip_b200_ext as _ext
+from .tensor import Tensor
+from .util import broadcast_shape
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def world():
+    dist = _dist()
+    return (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+
+
+def shard_bounds(span: int, rank: int, size: int):
+    """Global coordinate range of `rank` (eval::partition_pool, eval.hpp:452-456)."""
+    return (rank * span) // size, ((rank + 1) * span) // size
+
+
+def _device():
+    import torch
+    dist = _dist()
+    if dist.is_initialized() and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def _all_gather_i64(values):
+    import torch
+    dist = _dist()
+    rank, size = world()
+    mine = torch.tensor(list(values), dtype=torch.int64, device=_device())
+    if size == 1:
+        return mine.cpu().numpy()[None, :]
+    out = torch.empty(size * len(values), dtype=torch.int64, device=_device())
+    dist.all_gather_into_tensor(out, mine)
+    return out.cpu().numpy().reshape(size, len(values))
+
+
+def _payload_bits(vals: np.ndarray) -> np.ndarray:
+    if vals.dtype == np.float32:
+        return vals.view(np.uint32).astype(np.int64)
+    return vals.astype(np.int64) & 0xFFFFFFFF
+
+
+class ShardedTensor:
+    """A flat RLE array sharded by coordinate range; `local` holds this rank's shard."""
+
+    def __init__(self, local: Tensor, global_span: int):
+        self.local = local
+        self.global_span = int(global_span)
+        self.rank, self.size = world()
+        lo, hi = shard_bounds(self.global_span, self.rank, self.size)
+        assert len(local) == hi - lo, f"shard length {len(local)} != {hi - lo}"
+        self.offset = lo
+
+    @classmethod
+    def from_global_runs(cls, ends, vals, global_span=None):
+        """Every rank passes the same GLOBAL run arrays (int64 ends allowed) and keeps its
+        coordinate slice: binary search of the slice's first/last run (SimpleSource::split,
+        eval.hpp:281-287) + re-basing to local coordinates."""
+        ends = np.asarray(ends, dtype=np.int64)
+        vals = np.asarray(vals)
+        span = int(ends[-1]) if global_span is None else int(global_span)
+        rank, size = world()
+        lo, hi = shard_bounds(span, rank, size)
+        r0 = int(np.searchsorted(ends, lo, side="right"))
+        r1 = int(np.searchsorted(ends, hi - 1, side="right"))
+        le = np.minimum(ends[r0:r1 + 1], hi) - lo
+        cls_name = {np.dtype(np.int32): "IntArray", np.dtype(np.float32): "FloatArray",
+                    np.dtype(np.bool_): "BoolArray"}[vals.dtype]
+        arr = getattr(_ext, cls_name)._from_runs(le.astype(np.int32), np.ascontiguousarray(vals[r0:r1 + 1]))
+        return cls(Tensor(shape=(hi - lo,), val=arr), span)
+
+    def map(self, fn, *others):
+        """Element-wise op on co-partitioned shards: purely local."""
+        return ShardedTensor(fn(self.local, *[o.local for o in others]), self.global_span)
+
+    # ---- stitch: fuse_stores across ranks ----------------------------------------------
+    def stitch(self, bitwise=True):
+        """-> (runs this rank contributes, global index of its first run, global run count).
+        A rank's last run is dropped when the next shard starts with an equal value."""
+        src = self.local.eval() if bitwise else self.local
+        ends, vals = src.to_runs()
+        bits = _payload_bits(vals)
+        table = _all_gather_i64([int(bits[0]), int(bits[-1]), len(ends)])
+        counts = table[:, 2].copy()
+        for r in range(self.size - 1):
+            if table[r, 1] == table[r + 1, 0]:
+                counts[r] -= 1          # eval.hpp:581-588
+        first = int(counts[:self.rank].sum())
+        keep = int(counts[self.rank])
+        return (ends[:keep], vals[:keep]), first, int(counts.sum())
+
+    def gather_global(self, bitwise=True):
+        """All ranks -> the global (int64 ends, vals) run arrays (tests / small outputs)."""
+        import torch
+        dist = _dist()
+        (ends, vals), _, total = self.stitch(bitwise)
+        gl = ends.astype(np.int64) + self.offset
+        if self.size == 1:
+            return gl, vals
+        objs = [None] * self.size
+        dist.all_gather_object(objs, (gl, vals))
+        # a dropped last run extends its successor: the successor's run simply starts earlier,
+        # which the end-only encoding expresses by the drop itself
+        return np.concatenate([o[0] for o in objs]), np.concatenate([o[1] for o in objs])
+
+    # ---- reductions -----------------------------------------------------------------------
+    def sum(self):
+        import torch
+        dist = _dist()
+        from . import reduce as red
+        local = red.sum(self.local)
+        if self.size == 1:
+            return local
+        if self.local.dtype is float:
+            t = torch.tensor([float(local)], dtype=torch.float64, device=_device())
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return float(np.float32(t.item()))
+        t = torch.tensor([int(local) & 0xFFFFFFFF], dtype=torch.int64, device=_device())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        v = int(t.item()) & 0xFFFFFFFF           # int32 sums wrap mod 2^32
+        return v - (1 << 32) if v >= (1 << 31) else v
+
+    def _extreme(self, which):
+        import torch
+        dist = _dist()
+        from . import reduce as red
+        local = red.maximum(self.local) if which == "max" else red.minimum(self.local)
+        if self.size == 1:
+            return local
+        t = torch.tensor([float(local)], dtype=torch.float64, device=_device())
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if which == "max" else dist.ReduceOp.MIN)
+        return self.local.dtype(t.item())
+
+    def max(self):
+        return self._extreme("max")
+
+    def min(self):
+        return self._extreme("min")
+
+
+# ---- z-slab convolution with halo exchange ------------------------------------------------
+
+def _exchange_slices(lo_slice: Tensor, hi_slice: Tensor):
+    """Send my lowest z-slice to rank-1 and my highest to rank+1 (as runs); receive theirs.
+    Returns (slice from rank-1 or None, slice from rank+1 or None)."""
+    import torch
+    dist = _dist()
+    rank, size = world()
+    dev = _device()
+
+    def pack(t):
+        e, v = t.to_runs()
+        v32 = v.view(np.int32) if v.dtype == np.float32 else v.astype(np.int32)
+        return torch.from_numpy(np.concatenate([[len(e)], e, v32]).astype(np.int32)).to(dev)
+
+    def unpack(buf, like: Tensor, shape):
+        a = buf.cpu().numpy()
+        n = int(a[0])
+        e, v = a[1:1 + n], a[1 + n:1 + 2 * n]
+        if like.dtype is float:
+            arr = _ext.FloatArray._from_runs(e, v.view(np.float32))
+        elif like.dtype is bool:
+            arr = _ext.BoolArray._from_runs(e, v.astype(np.bool_))
+        else:
+            arr = _ext.IntArray._from_runs(e, v)
+        return Tensor(shape=shape, val=arr)
+
+    plane = lo_slice.shape
+    cap = 2 * int(np.prod(plane)) + 1              # worst case: one run per voxel
+    from_lo = from_hi = None
+    ops, bufs = [], {}
+    if rank > 0:
+        bufs["send_lo"] = pack(lo_slice)
+        bufs["recv_lo"] = torch.zeros(cap, dtype=torch.int32, device=dev)
+        ops.append(dist.P2POp(dist.isend, _padded(bufs["send_lo"], cap, dev), rank - 1))
+        ops.append(dist.P2POp(dist.irecv, bufs["recv_lo"], rank - 1))
+    if rank < size - 1:
+        bufs["send_hi"] = pack(hi_slice)
+        bufs["recv_hi"] = torch.zeros(cap, dtype=torch.int32, device=dev)
+        ops.append(dist.P2POp(dist.isend, _padded(bufs["send_hi"], cap, dev), rank + 1))
+        ops.append(dist.P2POp(dist.irecv, bufs["recv_hi"], rank + 1))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    if rank > 0:
+        from_lo = unpack(bufs["recv_lo"], lo_slice, plane)
+    if rank < size - 1:
+        from_hi = unpack(bufs["recv_hi"], hi_slice, plane)
+    return from_lo, from_hi
+
+
+def _padded(buf, cap, dev):
+    import torch
+    out = torch.zeros(cap, dtype=torch.int32, device=dev)
+    out[:buf.numel()] = buf
+    return out
+
+
+def conv_3d_slab(local: Tensor, kernel: Tensor, padding=0, fill=0):
+    """conv_3d (src/pyskip/convolve.py:39-59) of a volume partitioned along z: `local` is
+    this rank's z-slab (shape (X, Y, Zloc)).  Requires an odd kernel with padding =
+    kernel // 2 along z (the "same" convolution of the BASELINE configs), so every rank's
+    output slab has the thickness of its input slab."""
+    from .convolve import conv_3d
+    rank, size = world()
+    kx, ky, kz = kernel.shape
+    px, py, pz = broadcast_shape(3, padding)
+    assert kz % 2 == 1 and pz == kz // 2, "slab convolution needs padding == kernel // 2 along z"
+    X, Y, Z = local.shape
+    assert Z >= pz
+    if size == 1:
+        return conv_3d(local, kernel, padding=padding, fill=fill)
+    halo_lo, halo_hi = None, None
+    if pz > 0:
+        halo_lo, halo_hi = _exchange_slices(local[:, :, 0:pz], local[:, :, Z - pz:Z])
+    padded = Tensor(shape=(X + 2 * px, Y + 2 * py, Z + 2 * pz), dtype=local.dtype, val=fill)
+    padded[px:px + X, py:py + Y, pz:pz + Z] = local
+    if halo_lo is not None:
+        padded[px:px + X, py:py + Y, 0:pz] = halo_lo
+    if halo_hi is not None:
+        padded[px:px + X, py:py + Y, pz + Z:pz + Z + pz] = halo_hi
+    return conv_3d(padded.eval(), kernel, padding=0, fill=fill)
