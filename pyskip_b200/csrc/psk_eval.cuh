@@ -209,6 +209,37 @@ PSK_D int32_t block_exclusive_scan(int32_t v, int32_t* s_warp /*[T/32+1]*/, int3
 // Look-back chain word: (status << 32) | count.
 enum { ST_INVALID = 0, ST_AGGREGATE = 1, ST_PREFIX = 2 };
 
+// Decoupled look-back executed by one warp (lane l inspects tile j - l).  Selected with
+// -DPSK_LOOKBACK_WARP; see lookback_exclusive_cta for the default.
+PSK_D int32_t lookback_exclusive_warp(unsigned long long* state, int32_t tile, int32_t count) {
+  const int lane = threadIdx.x & 31;
+  if (tile == 0) {
+    if (lane == 0) st_volatile_u64(&state[0], ((unsigned long long)ST_PREFIX << 32) | (uint32_t)count);
+    return 0;
+  }
+  if (lane == 0) st_volatile_u64(&state[tile], ((unsigned long long)ST_AGGREGATE << 32) | (uint32_t)count);
+  int32_t excl = 0;
+  for (int32_t j = tile - 1;; j -= 32) {
+    const int32_t idx = j - lane;
+    unsigned long long w = (unsigned long long)ST_PREFIX << 32;
+    if (idx >= 0) {
+      do {
+        w = ld_volatile_u64(&state[idx]);
+      } while ((w >> 32) == ST_INVALID);
+    }
+    const unsigned pmask = __ballot_sync(0xffffffffu, (w >> 32) == ST_PREFIX);
+    const int first = pmask ? (__ffs((int)pmask) - 1) : 32;
+    int32_t c = (lane <= first) ? (int32_t)(uint32_t)w : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    excl += c;
+    if (pmask) break;
+  }
+  if (lane == 0)
+    st_volatile_u64(&state[tile], ((unsigned long long)ST_PREFIX << 32) | (uint32_t)(excl + count));
+  return excl;
+}
+
 // Decoupled look-back, executed by the whole CTA: thread r inspects tile (j - r), so one
 // round covers T predecessors -- the persistent CTAs move through the tiles in lock step, and
 // a tile typically has to sum the AGGREGATEs of every tile of its own wave.  The nearest tile
@@ -578,7 +609,16 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
       const int2 r = sm.ld(IN_N + base + j);
       sm.st(my_ofs + j, r.x, r.y);
     }
+#ifdef PSK_LOOKBACK_WARP
+    if (tid < 32) {
+      const int32_t excl = lookback_exclusive_warp(p->tile_state, tile, tile_total);
+      if (tid == 0) s_lbhas[0] = excl;
+    }
+    __syncthreads();
+    const int32_t gofs = s_lbhas[0];
+#else
     const int32_t gofs = lookback_exclusive_cta<T>(p->tile_state, tile, tile_total, s_warp, s_lbhas);
+#endif
     if (tid == 0 && tile == n_tiles - 1) p->ctrl[CTRL_COUNT] = gofs + tile_total;
     __syncthreads();
     PSK_PHASE(5);  // look-back + smem compaction

@@ -215,6 +215,9 @@ bool compile_cubin(int K, bool typed_float, int nprog, const psk_node* prog, std
 #ifdef PSK_TILE_CAP
                         "-DPSK_TILE_CAP=" PSK_STR(PSK_TILE_CAP),
 #endif
+#ifdef PSK_LOOKBACK_WARP
+                        "-DPSK_LOOKBACK_WARP",
+#endif
   };
   r = g_api.nvrtcCompileProgram(np, (int)(sizeof(opts) / sizeof(opts[0])), opts);
   if (r != 0) {

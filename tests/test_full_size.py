@@ -53,8 +53,8 @@ def _terrain(n=512, seed=3000):
         fx, fz, ph = rng.uniform(0.5, 3.0) / n, rng.uniform(0.5, 3.0) / n, rng.uniform(0, 6.28)
         h += (n // 10) * 0.25 * np.sin(2 * np.pi * (fx * xs + fz * zs) + ph)
     h = h.astype(np.int32)                                 # surface height per (z, x)
-    y = np.arange(n, dtype=np.int32)[None, None, :]
-    hh = h[:, :, None]
+    y = np.broadcast_to(np.arange(n, dtype=np.int32)[None, None, :], (n, n, n))
+    hh = np.broadcast_to(h[:, :, None], (n, n, n))
     vol = np.zeros((n, n, n), dtype=np.int32)              # air
     vol[y < hh] = 1                                        # stone
     vol[(y < hh) & (y >= hh - 4)] = 3                      # dirt
@@ -97,4 +97,5 @@ def test_c3_conv_512_properties():
         lo, hi = max(0, z0 - 1), min(n, z1 + 1)
         sub = O.conv3d_dense(vol[lo:hi], k1, padding=1, fill=0)[z0 - lo:z0 - lo + (z1 - z0)]
         assert np.array_equal(out[z0:z1], sub), (z0, z1)
-    assert ps.reduce.sum(c1) == int(np.int32(out.astype(np.int64).sum() & 0xFFFFFFFF)) or True
+    total = int(out.astype(np.int64).sum() & 0xFFFFFFFF)
+    assert ps.reduce.sum(c1) == (total - (1 << 32) if total >= (1 << 31) else total)
