@@ -321,21 +321,106 @@ struct SrcDesc {           // the per-source fields the tile loop needs, hoisted
   int32_t e;
 };
 
-// warp 0: take the next ticket and fetch that tile's bounds into *d (no barrier here)
-PSK_D void fetch_tile_desc(DPlan* p, TileDesc* d, int k, int32_t n_tiles) {
+// Bounds of a tile held in the registers of one warp while the loads are in flight (lane i
+// holds source i's bounds), written to shared memory only when the tile loop is ready for it.
+struct DescRegs {
+  int32_t tile, lo, hi, b0, b1;
+};
+
+// one warp: take the next ticket and start fetching that tile's bounds (no barrier, and no
+// use of the loaded values: they stay in flight until store_tile_desc)
+PSK_D DescRegs fetch_tile_desc(DPlan* p, int k, int32_t n_tiles) {
   const int lane = threadIdx.x & 31;
-  int32_t tile = 0;
-  if (lane == 0) tile = atomicAdd(&p->ctrl[CTRL_TICKET], 1);
-  tile = __shfl_sync(0xffffffffu, tile, 0);
-  if (lane == 0) d->tile = tile;
-  if (tile < n_tiles) {
+  DescRegs r;
+  r.tile = 0;
+  r.lo = r.hi = r.b0 = r.b1 = 0;
+  if (lane == 0) r.tile = atomicAdd(&p->ctrl[CTRL_TICKET], 1);
+  r.tile = __shfl_sync(0xffffffffu, r.tile, 0);
+  if (r.tile < n_tiles) {
     if (lane < k) {
-      d->b0[lane] = p->bounds[tile * k + lane];
-      d->b1[lane] = p->bounds[(tile + 1) * k + lane];
+      r.b0 = p->bounds[r.tile * k + lane];
+      r.b1 = p->bounds[(r.tile + 1) * k + lane];
     }
     if (lane == 0) {
-      d->lo = tile == 0 ? 0 : p->tile_hi[tile - 1];
-      d->hi = p->tile_hi[tile];
+      r.lo = r.tile == 0 ? 0 : p->tile_hi[r.tile - 1];
+      r.hi = p->tile_hi[r.tile];
+    }
+  }
+  return r;
+}
+
+PSK_D void store_tile_desc(const DescRegs& r, TileDesc* d, int k) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) {
+    d->tile = r.tile;
+    d->lo = r.lo;
+    d->hi = r.hi;
+  }
+  if (lane < k) {
+    d->b0[lane] = r.b0;
+    d->b1[lane] = r.b1;
+  }
+}
+
+// Where the runs of a tile go in the shared tile buffer: sources without a view occupy the
+// flat slots [0, flat_total) back to back (slice + one look-ahead run each); sources with a
+// view are appended behind them by the staging pass that maps and filters them.
+struct TileLayout {
+  int32_t off[PSK_MAX_SOURCES + 1];
+  int32_t len[PSK_MAX_SOURCES];  // staged runs (excl. look-ahead)
+  int32_t flat_total;
+};
+
+// one warp: layout of the view-less sources of tile d
+PSK_D void compute_layout(const TileDesc& d, const SrcDesc* src, int k, TileLayout* L) {
+  const int lane = threadIdx.x & 31;
+  int32_t len = 0;
+  if (lane < k && src[lane].nviews == 0) len = d.b1[lane] - d.b0[lane] + 1;  // + look-ahead
+  int32_t inc = len;
+#pragma unroll
+  for (int dd = 1; dd < 32; dd <<= 1) {
+    int32_t o = __shfl_up_sync(0xffffffffu, inc, dd);
+    if (lane >= dd) inc += o;
+  }
+  if (lane < k) {
+    L->off[lane] = inc - len;
+    L->len[lane] = len ? len - 1 : 0;
+  }
+  if (lane == 31) L->flat_total = inc;
+}
+
+// all threads: issue the global loads of the tile's view-less sources into registers (flat
+// slot j = tid + u*T).  Nothing waits on them here; they are stored to shared memory one
+// tile later, so the HBM latency overlaps the merge of the tile in front.
+template <int K, int T, int NB>
+PSK_D void issue_tile_loads(const TileDesc& d, const TileLayout& L, const SrcDesc* src, int k, int32_t limit,
+                            int2 (&pr)[NB]) {
+  const int32_t used = L.flat_total;
+#pragma unroll
+  for (int u = 0; u < NB; ++u) {
+    const int32_t j = (int32_t)threadIdx.x + u * T;
+    pr[u] = make_int2(kSentinel, 0);  // no run beyond the tile: sentinel look-ahead
+    if (j < used && used <= limit) {
+      // which source owns flat slot j: last i with off[i] <= j (view sources have zero slots
+      // here and are never the last such i)
+      int i = 0;
+      if (K <= 8) {
+#pragma unroll
+        for (int q = 1; q < K; ++q) i += (q < k && L.off[q] <= j) ? 1 : 0;
+      } else {
+        int l = 0, h = k - 1;
+        while (l < h) {
+          int mid = (l + h + 1) >> 1;
+          if (L.off[mid] <= j) l = mid; else h = mid - 1;
+        }
+        i = l;
+      }
+      const int32_t r = j - L.off[i];
+      const int32_t idx = d.b0[i] + r;
+      if (r < L.len[i] || idx < src[i].e) {
+        pr[u].x = ld_nc(src[i].ends + idx);
+        pr[u].y = (int32_t)ld_nc(src[i].vals + idx);
+      }
     }
   }
 }
@@ -353,13 +438,15 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
   PSK_DYN_SMEM(smem_raw);
   const SmemPairs sm(smem_raw);
 
-  __shared__ TileDesc s_desc[2];
+  __shared__ TileDesc s_desc[3];   // tile being merged, tile being loaded, tile being fetched
+  __shared__ TileLayout s_layout[2];
   __shared__ SrcDesc s_src[PSK_MAX_SOURCES];
-  __shared__ int32_t s_off[PSK_MAX_SOURCES + 1];  // start of each source's slice in the tile buffer
-  __shared__ int32_t s_len[PSK_MAX_SOURCES];      // staged runs of each source (excl. look-ahead)
   __shared__ int32_t s_warp[T / 32 + 2];
   __shared__ int32_t s_lbhas[T / 32];
-  __shared__ int32_t s_carry, s_fail, s_flat_total;
+  __shared__ int32_t s_carry;
+
+  constexpr int NB = (IN_N + T - 1) / T;  // flat slots per thread
+  int2 pr[NB];                            // the NEXT tile's runs, in flight
 
   const int tid = threadIdx.x;
   const int k = p->k;
@@ -375,85 +462,50 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     s_src[tid].nviews = s.nviews;
     s_src[tid].e = s.e;
   }
-  // Persistent CTAs that start together stay in lock step (same phase at the same time: HBM
-  // bursts, then idles, and every tile waits in the look-back for its whole wave).  A start
-  // delay proportional to the CTA index spreads them over one tile period; from then on a
-  // tile's predecessors were started earlier and have published by the time it looks back.
+  // Persistent CTAs that start together stay in lock step; an optional start delay per CTA
+  // index (PSKB200_STAGGER_NS, default 0) de-phases them.
   if (p->stagger_ns > 0 && blockIdx.x > 0) sleep_ns((unsigned)(p->stagger_ns * (int)blockIdx.x));
-  if (tid < 32) fetch_tile_desc(p, &s_desc[0], k, n_tiles);
+  // ---- pipeline prologue: descriptors of the first two tiles, data of the first ----------
+  if (tid < 32) {
+    store_tile_desc(fetch_tile_desc(p, k, n_tiles), &s_desc[0], k);
+    store_tile_desc(fetch_tile_desc(p, k, n_tiles), &s_desc[1], k);
+  }
   __syncthreads();
+  if (tid < 32 && s_desc[0].tile < n_tiles) compute_layout(s_desc[0], s_src, k, &s_layout[0]);
+  __syncthreads();
+  if (s_desc[0].tile < n_tiles) issue_tile_loads<K, T, NB>(s_desc[0], s_layout[0], s_src, k, IN_N, pr);
 
   PSK_PHASE_DECL;
   for (int it = 0;; ++it) {
-    const TileDesc& d = s_desc[it & 1];
+    const TileDesc& d = s_desc[it % 3];
+    const TileDesc& dn = s_desc[(it + 1) % 3];
+    TileLayout& lay = s_layout[it & 1];
+    int32_t* const s_off = lay.off;
+    int32_t* const s_len = lay.len;
     const int32_t tile = d.tile;
     if (tile >= n_tiles) break;
     const int32_t lo = d.lo, hi = d.hi;
+    const bool next_valid = dn.tile < n_tiles;
 
-    // ---- slice offsets: sources without a view are copied in one flat pass ---------------
-    if (tid < 32) {
-      int32_t len = 0;
-      if (tid < k && s_src[tid].nviews == 0) len = d.b1[tid] - d.b0[tid] + 1;  // + look-ahead
-      int32_t inc = len;
-#pragma unroll
-      for (int dd = 1; dd < 32; dd <<= 1) {
-        int32_t o = __shfl_up_sync(0xffffffffu, inc, dd);
-        if (tid >= dd) inc += o;
-      }
-      if (tid < k) {
-        s_off[tid] = inc - len;
-        s_len[tid] = len ? len - 1 : 0;
-      }
-      if (tid == 31) s_flat_total = inc;
-      if (tid == 0) s_fail = 0;
-    } else if (tid < 64) {
-      // meanwhile warp 1 takes the next ticket and fetches the next tile's bounds
-      fetch_tile_desc(p, &s_desc[(it + 1) & 1], k, n_tiles);
-    }
-    __syncthreads();
-    PSK_PHASE(0);
-    int32_t used = s_flat_total;
+    // ---- the tile's runs arrive from registers; meanwhile warp 0 lays out the next tile and
+    //      warp 1 starts fetching the bounds of the tile after that -----------------------
+    int32_t used = lay.flat_total;
     bool fail = used > IN_N;
     if (!fail) {
-      // All global loads of a batch are issued before any shared store (ld.global.nc cannot
-      // alias the staging buffer), so a thread keeps kStageBatch x 2 loads in flight.
-      constexpr int kStageBatch = 8;
-      for (int32_t j0 = tid; j0 < used; j0 += T * kStageBatch) {
-        int2 pr[kStageBatch];
 #pragma unroll
-        for (int u = 0; u < kStageBatch; ++u) {
-          const int32_t j = j0 + u * T;
-          pr[u] = make_int2(kSentinel, 0);  // no run beyond the tile: sentinel look-ahead
-          if (j < used) {
-            // which source owns flat slot j: last i with s_off[i] <= j (view sources have
-            // zero slots here and are never the last such i)
-            int i = 0;
-            if (K <= 8) {
-#pragma unroll
-              for (int q = 1; q < K; ++q) i += (q < k && s_off[q] <= j) ? 1 : 0;
-            } else {
-              int l = 0, h = k - 1;
-              while (l < h) {
-                int mid = (l + h + 1) >> 1;
-                if (s_off[mid] <= j) l = mid; else h = mid - 1;
-              }
-              i = l;
-            }
-            const int32_t r = j - s_off[i];
-            const int32_t idx = d.b0[i] + r;
-            if (r < s_len[i] || idx < s_src[i].e) {
-              pr[u].x = ld_nc(s_src[i].ends + idx);
-              pr[u].y = (int32_t)ld_nc(s_src[i].vals + idx);
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < kStageBatch; ++u) {
-          const int32_t j = j0 + u * T;
-          if (j < used) sm.st(j, pr[u].x, pr[u].y);
-        }
+      for (int u = 0; u < NB; ++u) {
+        const int32_t j = tid + u * T;
+        if (j < used) sm.st(j, pr[u].x, pr[u].y);
       }
     }
+    DescRegs fetched;
+    fetched.tile = fetched.lo = fetched.hi = fetched.b0 = fetched.b1 = 0;
+    if (tid < 32) {
+      if (next_valid) compute_layout(dn, s_src, k, &s_layout[(it + 1) & 1]);
+    } else if (tid < 64) {
+      fetched = fetch_tile_desc(p, k, n_tiles);
+    }
+    PSK_PHASE(0);
     // ---- sources with a view: mapped ends, zero-length mapped runs dropped ---------------
     if (any_views && !fail) {
       for (int i = 0; i < k; ++i) {
@@ -499,6 +551,8 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     __syncthreads();
     PSK_PHASE(1);  // staging
     if (fail && tid == 0) p->ctrl[CTRL_ERROR] = 1;
+    // the next tile's loads go out now and land while this tile is merged
+    if (next_valid) issue_tile_loads<K, T, NB>(dn, s_layout[(it + 1) & 1], s_src, k, IN_N, pr);
 
     // ---- split the tile's coordinate range (lo, hi] over the threads --------------------
     const long long width = (long long)hi - lo;
@@ -631,6 +685,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     } else if (tid == 0) {
       p->ctrl[CTRL_ERROR] = 2;
     }
+    if (tid >= 32 && tid < 64) store_tile_desc(fetched, &s_desc[(it + 2) % 3], k);
     __syncthreads();
     PSK_PHASE(6);  // coalesced global write
   }
@@ -638,7 +693,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
 }
 
 template <int K>
-__global__ void __launch_bounds__(kTileThreads) k_merge_eval_interp(DPlan* p) {
+__global__ void __launch_bounds__(kTileThreads, 1) k_merge_eval_interp(DPlan* p) {
   __shared__ psk_node s_prog[PSK_MAX_PROGRAM];
   for (int i = threadIdx.x; i < p->nprog; i += blockDim.x) s_prog[i] = p->prog[i];
   __syncthreads();
