@@ -35,7 +35,7 @@ namespace psk {
 #define PSK_TILE_THREADS 512
 #endif
 #ifndef PSK_TILE_CAP
-#define PSK_TILE_CAP 6144
+#define PSK_TILE_CAP 8192
 #endif
 constexpr int kTileThreads = PSK_TILE_THREADS;
 constexpr int kTileCap = PSK_TILE_CAP;  // runs of all sources staged per tile (excl. look-ahead)
@@ -209,51 +209,22 @@ PSK_D int32_t block_exclusive_scan(int32_t v, int32_t* s_warp /*[T/32+1]*/, int3
 // Look-back chain word: (status << 32) | count.
 enum { ST_INVALID = 0, ST_AGGREGATE = 1, ST_PREFIX = 2 };
 
-// Decoupled look-back executed by one warp (lane l inspects tile j - l).  Selected with
-// -DPSK_LOOKBACK_WARP; see lookback_exclusive_cta for the default.
-PSK_D int32_t lookback_exclusive_warp(unsigned long long* state, int32_t tile, int32_t count) {
-  const int lane = threadIdx.x & 31;
-  if (tile == 0) {
-    if (lane == 0) st_volatile_u64(&state[0], ((unsigned long long)ST_PREFIX << 32) | (uint32_t)count);
-    return 0;
-  }
-  if (lane == 0) st_volatile_u64(&state[tile], ((unsigned long long)ST_AGGREGATE << 32) | (uint32_t)count);
-  int32_t excl = 0;
-  for (int32_t j = tile - 1;; j -= 32) {
-    const int32_t idx = j - lane;
-    unsigned long long w = (unsigned long long)ST_PREFIX << 32;
-    if (idx >= 0) {
-      do {
-        w = ld_volatile_u64(&state[idx]);
-      } while ((w >> 32) == ST_INVALID);
-    }
-    const unsigned pmask = __ballot_sync(0xffffffffu, (w >> 32) == ST_PREFIX);
-    const int first = pmask ? (__ffs((int)pmask) - 1) : 32;
-    int32_t c = (lane <= first) ? (int32_t)(uint32_t)w : 0;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    excl += c;
-    if (pmask) break;
-  }
-  if (lane == 0)
-    st_volatile_u64(&state[tile], ((unsigned long long)ST_PREFIX << 32) | (uint32_t)(excl + count));
-  return excl;
+PSK_D void publish_aggregate(unsigned long long* state, int32_t tile, int32_t count) {
+  // tile 0 has no predecessor: its aggregate is already its inclusive prefix
+  const unsigned long long st = tile == 0 ? ST_PREFIX : ST_AGGREGATE;
+  st_volatile_u64(&state[tile], (st << 32) | (uint32_t)count);
 }
 
 // Decoupled look-back, executed by the whole CTA: thread r inspects tile (j - r), so one
-// round covers T predecessors -- the persistent CTAs move through the tiles in lock step, and
-// a tile typically has to sum the AGGREGATEs of every tile of its own wave.  The nearest tile
-// that already published an inclusive PREFIX ends the walk.  Tiles are handed out by an
-// atomic ticket, so every predecessor is resident or finished and the spin cannot deadlock.
+// round covers T predecessors (with the write deferred by a tile, everything younger than
+// about two tile periods has only published an AGGREGATE).  The nearest tile that already
+// published an inclusive PREFIX ends the walk.  Tiles are handed out by an atomic ticket, so
+// every predecessor is resident or finished and the spin cannot deadlock.
 template <int T>
 PSK_D int32_t lookback_exclusive_cta(unsigned long long* state, int32_t tile, int32_t count,
                                      int32_t* s_sum /*[T/32]*/, int32_t* s_has /*[T/32]*/) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tile == 0) {
-    if (tid == 0) st_volatile_u64(&state[0], ((unsigned long long)ST_PREFIX << 32) | (uint32_t)count);
-    return 0;
-  }
-  if (tid == 0) st_volatile_u64(&state[tile], ((unsigned long long)ST_AGGREGATE << 32) | (uint32_t)count);
+  if (tile == 0) return 0;
   int32_t excl = 0;
   for (int32_t j = tile - 1;; j -= T) {
     const int32_t idx = j - tid;
@@ -268,6 +239,7 @@ PSK_D int32_t lookback_exclusive_cta(unsigned long long* state, int32_t tile, in
     int32_t c = (lane <= first) ? (int32_t)(uint32_t)w : 0;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    __syncthreads();  // s_sum / s_has free (previous round or other users of s_warp)
     if (lane == 0) {
       s_sum[warp] = c;
       s_has[warp] = pmask != 0;
@@ -281,12 +253,32 @@ PSK_D int32_t lookback_exclusive_cta(unsigned long long* state, int32_t tile, in
         break;
       }
     }
-    __syncthreads();
     if (done) break;
   }
+  __syncthreads();
   if (tid == 0)
     st_volatile_u64(&state[tile], ((unsigned long long)ST_PREFIX << 32) | (uint32_t)(excl + count));
   return excl;
+}
+
+// Resolve the global offset of a finished tile whose compacted spans wait at sm[region..] and
+// write them out (coalesced).  Called by the whole CTA.
+template <int T>
+PSK_D void flush_pending(DPlan* p, const SmemPairs& sm, int region, int32_t tile, int32_t total,
+                         int32_t n_tiles, int32_t* s_sum, int32_t* s_has) {
+  const int tid = threadIdx.x;
+  const int32_t gofs = lookback_exclusive_cta<T>(p->tile_state, tile, total, s_sum, s_has);
+  if (tid == 0 && tile == n_tiles - 1) p->ctrl[CTRL_COUNT] = gofs + total;
+  if (gofs + total <= p->out_capacity) {
+    for (int32_t j = tid; j < total; j += T) {
+      const int2 r = sm.ld(region + j);
+      p->out_ends[gofs + j] = r.x;
+      p->out_vals[gofs + j] = (uint32_t)r.y;
+    }
+  } else if (tid == 0) {
+    p->ctrl[CTRL_ERROR] = 2;
+  }
+  __syncthreads();  // the region may be overwritten now
 }
 
 // ---------------------------------------------------------------------------------------
@@ -445,6 +437,8 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
   __shared__ int32_t s_lbhas[T / 32];
   __shared__ int32_t s_carry;
 
+  constexpr int PEND = IN_N + CAP;        // third region: compacted spans awaiting their offset
+  int32_t pend_tile = -1, pend_total = 0;
   constexpr int NB = (IN_N + T - 1) / T;  // flat slots per thread
   int2 pr[NB];                            // the NEXT tile's runs, in flight
 
@@ -653,42 +647,28 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     }
 
     PSK_PHASE(3);  // thread 0's own merge loop
-    // ---- compaction: block scan, cross-tile look-back, coalesced write -------------------
+    // ---- compaction: block scan; the cross-tile look-back and the global write of a tile
+    //      are DEFERRED by one tile: its run count is published right after the scan, its
+    //      compacted spans wait in the third region of the tile buffer while the CTA merges
+    //      the next tile, and by the time it looks back every predecessor has long published
+    //      (no waiting on the slowest tile of the wave) ----------------------
     int32_t tile_total;
     const int32_t my_ofs = block_exclusive_scan<T>(n, s_warp, &tile_total);
     PSK_PHASE(4);  // waiting for the slowest thread + scan
-    // the input half of the tile buffer is dead (every thread passed the scan's barriers): reuse it as the compacted
-    // staging area so that the global write is fully coalesced
+    if (tid == 0) publish_aggregate(p->tile_state, tile, tile_total);
+    if (pend_tile >= 0) flush_pending<T>(p, sm, PEND, pend_tile, pend_total, n_tiles, s_warp, s_lbhas);
+    PSK_PHASE(5);  // look-back + global write of the previous tile
     for (int32_t j = 0; j < n; ++j) {
       const int2 r = sm.ld(IN_N + base + j);
-      sm.st(my_ofs + j, r.x, r.y);
+      sm.st(PEND + my_ofs + j, r.x, r.y);
     }
-#ifdef PSK_LOOKBACK_WARP
-    if (tid < 32) {
-      const int32_t excl = lookback_exclusive_warp(p->tile_state, tile, tile_total);
-      if (tid == 0) s_lbhas[0] = excl;
-    }
-    __syncthreads();
-    const int32_t gofs = s_lbhas[0];
-#else
-    const int32_t gofs = lookback_exclusive_cta<T>(p->tile_state, tile, tile_total, s_warp, s_lbhas);
-#endif
-    if (tid == 0 && tile == n_tiles - 1) p->ctrl[CTRL_COUNT] = gofs + tile_total;
-    __syncthreads();
-    PSK_PHASE(5);  // look-back + smem compaction
-    if (gofs + tile_total <= p->out_capacity) {
-      for (int32_t j = tid; j < tile_total; j += T) {
-        const int2 r = sm.ld(j);
-        p->out_ends[gofs + j] = r.x;
-        p->out_vals[gofs + j] = (uint32_t)r.y;
-      }
-    } else if (tid == 0) {
-      p->ctrl[CTRL_ERROR] = 2;
-    }
+    pend_tile = tile;
+    pend_total = tile_total;
     if (tid >= 32 && tid < 64) store_tile_desc(fetched, &s_desc[(it + 2) % 3], k);
     __syncthreads();
-    PSK_PHASE(6);  // coalesced global write
+    PSK_PHASE(6);  // smem compaction
   }
+  if (pend_tile >= 0) flush_pending<T>(p, sm, PEND, pend_tile, pend_total, n_tiles, s_warp, s_lbhas);
   PSK_PHASE_FLUSH;
 }
 
@@ -702,6 +682,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_merge_eval_interp(DPlan* p)
   else merge_eval_tile_loop<K, false>(p, ev);
 }
 
-constexpr unsigned kMergeEvalSmemBytes = ((kTileCap + PSK_MAX_SOURCES) + kTileCap) * 8;
+constexpr unsigned kMergeEvalSmemBytes = ((kTileCap + PSK_MAX_SOURCES) + 2 * kTileCap) * 8;
 
 }  // namespace psk
