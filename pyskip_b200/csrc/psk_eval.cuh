@@ -41,6 +41,14 @@ constexpr int kTileThreads = PSK_TILE_THREADS;
 constexpr int kTileCap = PSK_TILE_CAP;  // runs of all sources staged per tile (excl. look-ahead)
 constexpr int kSentinel = 0x7fffffff;
 
+// dynamic shared memory of k_merge_eval: in[CAP + 32] | out[CAP] | pending[CAP] (8-byte pairs)
+constexpr unsigned kMergeEvalSmemBytes = ((kTileCap + PSK_MAX_SOURCES) + 2 * kTileCap) * 8;
+// CTAs that stay resident per SM (227 KB of shared memory, 2048 threads); also the minimum
+// the compiler must leave room for in the register file
+constexpr int kCtasBySmem = (227 * 1024) / (int)(kMergeEvalSmemBytes + 4096);
+constexpr int kCtasByThreads = 2048 / kTileThreads;
+constexpr int kCtasPerSm = kCtasBySmem < kCtasByThreads ? (kCtasBySmem < 1 ? 1 : kCtasBySmem) : kCtasByThreads;
+
 // Development aid (-DPSK_PHASE_TIMING, tools/phase_profile.py): thread 0 of every CTA adds the
 // clock64() cycles it spends in each phase of the tile loop to p->phase[].  Not compiled into
 // the product library.
@@ -673,7 +681,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
 }
 
 template <int K>
-__global__ void __launch_bounds__(kTileThreads, 1) k_merge_eval_interp(DPlan* p) {
+__global__ void __launch_bounds__(kTileThreads, kCtasPerSm) k_merge_eval_interp(DPlan* p) {
   __shared__ psk_node s_prog[PSK_MAX_PROGRAM];
   for (int i = threadIdx.x; i < p->nprog; i += blockDim.x) s_prog[i] = p->prog[i];
   __syncthreads();
@@ -682,6 +690,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_merge_eval_interp(DPlan* p)
   else merge_eval_tile_loop<K, false>(p, ev);
 }
 
-constexpr unsigned kMergeEvalSmemBytes = ((kTileCap + PSK_MAX_SOURCES) + 2 * kTileCap) * 8;
+
 
 }  // namespace psk

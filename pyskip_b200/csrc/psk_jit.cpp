@@ -176,7 +176,7 @@ std::string gen_source(int K, bool typed_float, int nprog, const psk_node* prog)
   src += "  }\n};\n}  // namespace psk\n";
   snprintf(buf, sizeof buf,
            "  psk::merge_eval_tile_loop<%d, %s>(p, ev);\n}\n", K, typed_float ? "true" : "false");
-  src += "extern \"C\" __global__ void __launch_bounds__(psk::kTileThreads, 1) psk_jit_merge_eval(psk::DPlan* p) {\n"
+  src += "extern \"C\" __global__ void __launch_bounds__(psk::kTileThreads, psk::kCtasPerSm) psk_jit_merge_eval(psk::DPlan* p) {\n"
          "  psk::JitEval ev;\n";
   src += inits;
   src += buf;

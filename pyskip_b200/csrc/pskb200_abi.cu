@@ -804,10 +804,7 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
     LAUNCH(k_sample_rank, (unsigned)((max_samples + 255) / 256), 256, 0, d_plan);
     LAUNCH(k_tile_bounds, (unsigned)(((max_tiles + 1) * k + 255) / 256), 256, 0, d_plan);
     // persistent grid: as many CTAs as stay resident (shared memory / thread limits)
-    int per_sm = (227 * 1024) / (int)(kMergeEvalSmemBytes + 2048);
-    if (per_sm > 2048 / kTileThreads) per_sm = 2048 / kTileThreads;
-    if (per_sm < 1) per_sm = 1;
-    int64_t grid = per_sm * (int64_t)g.sm_count;
+    int64_t grid = kCtasPerSm * (int64_t)g.sm_count;
     if (grid > max_tiles) grid = max_tiles;
     if (g.profile) cudaEventRecord(g.pev0, g.stream);
     bool launched = false;
