@@ -78,6 +78,8 @@ class ClockSampler:
         self.gpu_index = gpu_index
 
     def start(self):
+        if os.environ.get("BENCH_NO_CLOCKS"):
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",

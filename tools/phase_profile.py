@@ -32,7 +32,7 @@ out = os.path.join(ROOT, "gpurun_out", f"libpskb200_phase_{args.threads}_{args.c
 os.makedirs(os.path.dirname(out), exist_ok=True)
 if args.build_only or not os.path.exists(out):
     B.gen_jit_embed()
-    subprocess.check_call([B.nvcc_path()] + B.NVCC_FLAGS + defs + ["-I" + B.CSRC,
+    subprocess.check_call([B.nvcc_path()] + B.NVCC_FLAGS + B.nvrtc_define() + defs + ["-I" + B.CSRC,
                           os.path.join(B.CSRC, "pskb200_abi.cu"), os.path.join(B.CSRC, "psk_jit.cpp"),
                           "-o", out, "-ldl"])
     if args.build_only:
