@@ -245,16 +245,23 @@ def main():
         if dist is None:
             return res.nruns
         first, last, n = lib.store_boundary(res)
-        mine = torch.tensor([first, last, n], dtype=torch.int64, device="cuda")
-        allv = torch.empty(world * 3, dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(allv, mine)
-        allv = allv.view(world, 3).cpu()
+        st_host[0], st_host[1], st_host[2] = first, last, n
+        st_mine.copy_(st_host, non_blocking=True)
+        dist.all_gather_into_tensor(st_all, st_mine)
+        st_all_host.copy_(st_all, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        allv = st_all_host.view(world, 3)
         counts = allv[:, 2].clone()
         for r in range(world - 1):
             if allv[r, 1] == allv[r + 1, 0]:
                 counts[r] -= 1
         return int(counts.sum())
 
+    if dist is not None:
+        st_host = torch.zeros(3, dtype=torch.int64, pin_memory=True)
+        st_mine = torch.zeros(3, dtype=torch.int64, device="cuda")
+        st_all = torch.zeros(world * 3, dtype=torch.int64, device="cuda")
+        st_all_host = torch.zeros(world * 3, dtype=torch.int64, pin_memory=True)
     resident = upload()
     srcs = [(s, []) for s in resident]
 
@@ -301,20 +308,38 @@ def main():
     value = world * runs_in_step / (ms_step * 1e-3) / 1e9
 
     # ---- e2e: pinned host -> device -> eval -> runs back on the host ----------------------
-    def step_e2e():
-        st = upload()
-        r = lib.eval([(s, []) for s in st], prog, A.F32, A.EQ_BITWISE)
-        n = r.nruns
-        lib._chk(lib.c.psk_store_runs(A.C.c_void_p(r.h), A.C.c_void_p(out_e.data_ptr()),
-                                      A.C.c_void_p(out_v.data_ptr())))
-        return n
+    # Every step uploads its 4 operands from pinned host memory (320 MB), evaluates, and
+    # downloads the result runs into pinned host memory.  The transfers use the library's
+    # copy streams (psk_store_from_runs_async / psk_store_runs_async), so step i+1's upload
+    # and step i's download overlap step i+1's kernels (PCIe is full duplex); nothing is
+    # skipped or cached -- every byte moves every step, inside the timed region.
+    outs = [(out_e, out_v),
+            (torch.empty_like(out_e).pin_memory(), torch.empty_like(out_v).pin_memory())]
 
-    n_e2e = max(3, min(args.steps, 10))
-    step_e2e()
+    def upload_async():
+        return [lib.store_from_runs_async(pe.numpy(), pv.numpy()) for pe, pv in host]
+
+    def run_e2e(n):
+        pending = upload_async()
+        prev = None
+        n_out = 0
+        for i in range(n):
+            nxt = upload_async() if i + 1 < n else None
+            r = lib.eval([(s, []) for s in pending], prog, A.F32, A.EQ_BITWISE)
+            n_out = r.nruns
+            oe, ov = outs[i & 1]
+            lib.store_runs_async(r, oe.numpy(), ov.numpy())
+            prev = (r, pending)          # keep alive until their copies have been ordered
+            pending = nxt
+        lib.copy_synchronize()
+        lib.synchronize()
+        return n_out
+
+    n_e2e = max(4, min(args.steps, 12))
+    run_e2e(2)
     barrier()
     w0 = time.perf_counter()
-    for _ in range(n_e2e):
-        n_out = step_e2e()
+    n_out = run_e2e(n_e2e)
     barrier()
     e2e_s = (time.perf_counter() - w0) / n_e2e
     if dist is not None:

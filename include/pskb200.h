@@ -186,6 +186,16 @@ PSK_API psk_status psk_profile_read(double* merge_eval_ms, int64_t* evals, int64
 /* From host run arrays (core::Store ctor; validated: n>0, ends strictly increasing). */
 PSK_API psk_status psk_store_from_runs(psk_dtype dtype, int64_t nruns, const int32_t* ends,
                                        const void* vals, psk_store_t* out);
+/* Pipelined host transfers (I32 / F32 stores; host buffers should be pinned): the upload runs
+ * on a dedicated copy stream and the first psk_eval that consumes the store waits for it ON
+ * THE DEVICE; the download runs on a second copy stream.  With both, step i+1's upload and
+ * step i-1's download overlap step i's kernels (PCIe is full duplex).  Validation of the run
+ * ends happens on the device and is reported by the consuming psk_eval.
+ * psk_copy_synchronize() waits for both copy streams. */
+PSK_API psk_status psk_store_from_runs_async(psk_dtype dtype, int64_t nruns, const int32_t* ends,
+                                             const void* vals, psk_store_t* out);
+PSK_API psk_status psk_store_runs_async(psk_store_t s, int32_t* ends, void* vals);
+PSK_API psk_status psk_copy_synchronize(void);
 /* Same, from device arrays (copied device-to-device on the library stream). */
 PSK_API psk_status psk_store_from_device_runs(psk_dtype dtype, int64_t nruns,
                                               const int32_t* d_ends, const uint32_t* d_vals,

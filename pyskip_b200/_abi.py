@@ -104,7 +104,7 @@ def make_view(kind, shape, comps=None, scale=None, offset=None) -> View:
 _SYMBOLS = [
     "psk_last_error", "psk_version", "psk_is_simulator", "psk_init", "psk_device_count",
     "psk_synchronize", "psk_get_stream", "psk_set_stream", "psk_timer_start", "psk_timer_stop", "psk_launch_count",
-    "psk_live_bytes", "psk_profile", "psk_profile_read", "psk_set_jit_threshold", "psk_jit_launch_count", "psk_jit_compile_check", "psk_store_from_runs", "psk_store_from_device_runs", "psk_store_fill",
+    "psk_live_bytes", "psk_profile", "psk_profile_read", "psk_set_jit_threshold", "psk_jit_launch_count", "psk_jit_compile_check", "psk_store_from_runs", "psk_store_from_runs_async", "psk_store_runs_async", "psk_copy_synchronize", "psk_store_from_device_runs", "psk_store_fill",
     "psk_store_from_dense", "psk_store_from_dense_device", "psk_store_to_dense",
     "psk_store_to_dense_device", "psk_store_runs", "psk_store_nruns", "psk_store_span",
     "psk_store_dtype", "psk_store_device_ptrs", "psk_store_first_value", "psk_store_retain",
@@ -188,6 +188,8 @@ class Lib:
         c.psk_store_retain.argtypes = [C.c_void_p]
         c.psk_store_retain.restype = None
         c.psk_store_from_runs.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        c.psk_store_from_runs_async.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        c.psk_store_runs_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         c.psk_store_from_device_runs.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         c.psk_store_fill.argtypes = [C.c_int, C.c_int32, C.c_uint32, C.c_void_p]
         c.psk_store_from_dense.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
@@ -280,6 +282,23 @@ class Lib:
         self._chk(self.c.psk_store_from_runs(dt, len(ends), ends.ctypes.data_as(C.c_void_p),
                                              vals.ctypes.data_as(C.c_void_p), C.byref(h)))
         return Store(self, h.value)
+
+    def store_from_runs_async(self, ends, vals) -> Store:
+        """Upload on the copy stream; `ends` / `vals` must stay alive (ideally pinned) until the
+        first evaluation that consumes the store has returned."""
+        assert ends.dtype == np.int32 and vals.dtype in (np.int32, np.float32)
+        h = C.c_void_p()
+        self._chk(self.c.psk_store_from_runs_async(DTYPE_OF_NP[vals.dtype], len(ends), ends.ctypes.data_as(C.c_void_p),
+                                                   vals.ctypes.data_as(C.c_void_p), C.byref(h)))
+        return Store(self, h.value)
+
+    def store_runs_async(self, s: Store, ends_out, vals_out):
+        """Download on the second copy stream into caller-owned (pinned) buffers."""
+        self._chk(self.c.psk_store_runs_async(C.c_void_p(s.h), ends_out.ctypes.data_as(C.c_void_p),
+                                              vals_out.ctypes.data_as(C.c_void_p)))
+
+    def copy_synchronize(self):
+        self._chk(self.c.psk_copy_synchronize())
 
     def store_from_device_runs(self, dtype, nruns, d_ends, d_vals) -> Store:
         h = C.c_void_p()

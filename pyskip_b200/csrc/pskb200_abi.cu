@@ -32,6 +32,8 @@ struct psk_store_s {
   int32_t span = 0;
   int32_t* d_ends = nullptr;
   uint32_t* d_vals = nullptr;
+  cudaEvent_t ready = nullptr;  // async upload finished (waited on by the first consumer)
+  cudaEvent_t busy = nullptr;   // async download finished (waited on before the memory is freed)
 };
 
 namespace {
@@ -43,6 +45,8 @@ struct Ctx {
   int device = -1;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t h2d = nullptr, d2h = nullptr;  // copy streams of the *_async entry points
+  int32_t* d_async_err = nullptr;             // device flag: an async upload failed validation
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t pev0 = nullptr, pev1 = nullptr;  // bracket the merge/eval kernel when profiling
   bool profile = false;
@@ -105,6 +109,10 @@ psk_status do_init(int device) {
   if (device < 0 || device >= count) return fail(PSK_EINVAL, "device index out of range");
   CUDA_TRY(cudaSetDevice(device));
   CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&g.h2d, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&g.d2h, cudaStreamNonBlocking));
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&g.d_async_err), 16));
+  CUDA_TRY(cudaMemset(g.d_async_err, 0, 16));
   CUDA_TRY(cudaEventCreate(&g.ev0));
   CUDA_TRY(cudaEventCreate(&g.ev1));
   CUDA_TRY(cudaEventCreate(&g.pev0));
@@ -494,6 +502,57 @@ psk_status psk_store_from_runs(psk_dtype dtype, int64_t nruns, const int32_t* en
   return PSK_OK;
 }
 
+psk_status psk_store_from_runs_async(psk_dtype dtype, int64_t nruns, const int32_t* ends, const void* vals,
+                                     psk_store_t* out) {
+  NEED_INIT();
+  PSK_CHECK_ARG(out != nullptr && ends != nullptr && vals != nullptr);
+  PSK_CHECK_ARG(dtype == PSK_I32 || dtype == PSK_F32);  // 4-byte payloads only
+  PSK_CHECK_ARG(nruns > 0 && nruns < 0x7fffffffLL);
+  psk_store_s* s = new (std::nothrow) psk_store_s();
+  if (!s) return fail(PSK_ENOMEM, "out of host memory");
+  s->dtype = dtype;
+  s->capacity = nruns;
+  s->nruns = nruns;
+  s->span = ends[nruns - 1];  // host memory: readable here
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&s->d_ends), (size_t)nruns * 4, g.h2d);
+  if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&s->d_vals), (size_t)nruns * 4, g.h2d);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_ends, ends, (size_t)nruns * 4, cudaMemcpyHostToDevice, g.h2d);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_vals, vals, (size_t)nruns * 4, cudaMemcpyHostToDevice, g.h2d);
+  if (e == cudaSuccess) {
+    PSK_LAUNCH(k_validate_runs, (unsigned)((nruns + 255) / 256), 256, 0, g.h2d, s->d_ends, (int32_t)nruns, g.d_async_err);
+    g.launches.fetch_add(1, std::memory_order_relaxed);
+    e = cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventRecord(s->ready, g.h2d);
+  if (e != cudaSuccess) {
+    delete s;
+    return fail(PSK_ECUDA, std::string("psk_store_from_runs_async: ") + cudaGetErrorString(e));
+  }
+  g.live_bytes += nruns * 8;
+  *out = s;
+  return PSK_OK;
+}
+
+psk_status psk_store_runs_async(psk_store_t s, int32_t* ends, void* vals) {
+  NEED_INIT();
+  PSK_CHECK_ARG(s != nullptr && ends != nullptr && vals != nullptr);
+  PSK_CHECK_ARG(s->dtype == PSK_I32 || s->dtype == PSK_F32);
+  const size_t n = (size_t)s->nruns;
+  if (s->ready) CUDA_TRY(cudaStreamWaitEvent(g.d2h, s->ready, 0));
+  CUDA_TRY(cudaMemcpyAsync(ends, s->d_ends, n * 4, cudaMemcpyDeviceToHost, g.d2h));
+  CUDA_TRY(cudaMemcpyAsync(vals, s->d_vals, n * 4, cudaMemcpyDeviceToHost, g.d2h));
+  if (!s->busy) CUDA_TRY(cudaEventCreateWithFlags(&s->busy, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(s->busy, g.d2h));
+  return PSK_OK;
+}
+
+psk_status psk_copy_synchronize(void) {
+  NEED_INIT();
+  CUDA_TRY(cudaStreamSynchronize(g.h2d));
+  CUDA_TRY(cudaStreamSynchronize(g.d2h));
+  return PSK_OK;
+}
+
 psk_status psk_store_from_device_runs(psk_dtype dtype, int64_t nruns, const int32_t* d_ends,
                                       const uint32_t* d_vals, psk_store_t* out) {
   NEED_INIT();
@@ -654,6 +713,9 @@ void psk_store_retain(psk_store_t s) {
 void psk_store_release(psk_store_t s) {
   if (!s) return;
   if (s->ref.fetch_sub(1) == 1) {
+    // stream-ordered free on the library stream, after any copy still reading / writing it
+    if (s->ready) { cudaStreamWaitEvent(g.stream, s->ready, 0); cudaEventDestroy(s->ready); }
+    if (s->busy) { cudaStreamWaitEvent(g.stream, s->busy, 0); cudaEventDestroy(s->busy); }
     if (s->d_ends) cudaFreeAsync(s->d_ends, g.stream);
     if (s->d_vals) cudaFreeAsync(s->d_vals, g.stream);
     g.live_bytes -= s->capacity * 8;
@@ -698,6 +760,7 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
   int64_t span = -1;
   int64_t total_runs = 0;
   bool any_views = false;
+  bool used_async = false;
   for (int i = 0; i < k; ++i) {
     const psk_source& s = sources[i];
     PSK_CHECK_ARG(s.store != nullptr);
@@ -717,6 +780,12 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
       cur = o;
     }
     if (s.nviews) any_views = true;
+    if (s.store->ready) {  // uploaded by psk_store_from_runs_async: order the kernels after the copy
+      CUDA_TRY(cudaStreamWaitEvent(g.stream, s.store->ready, 0));
+      cudaEventDestroy(s.store->ready);
+      s.store->ready = nullptr;
+      used_async = true;
+    }
     // every source of a pool must share the output span (eval.hpp:400-403, lang.hpp:198)
     if (span < 0) span = cur;
     else if (span != cur) return fail(PSK_EINVAL, "sources have different spans");
@@ -826,6 +895,9 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(g.h_ctrl, hp.ctrl, CTRL_WORDS * 4, cudaMemcpyDeviceToHost, g.stream);
+  g.h_ctrl[8] = 0;
+  if (e == cudaSuccess && used_async)
+    e = cudaMemcpyAsync(g.h_ctrl + 8, g.d_async_err, 4, cudaMemcpyDeviceToHost, g.stream);
 #ifdef PSK_PHASE_TIMING
   if (e == cudaSuccess) e = cudaMemcpyAsync(g.h_ctrl + 16, hp.phase, 64, cudaMemcpyDeviceToHost, g.stream);
 #endif
@@ -834,6 +906,11 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
   if (e != cudaSuccess) {
     psk_store_release(res);
     return fail(PSK_ECUDA, std::string("psk_eval: ") + cudaGetErrorString(e));
+  }
+  if (g.h_ctrl[8] != 0) {
+    cudaMemsetAsync(g.d_async_err, 0, 4, g.stream);
+    psk_store_release(res);
+    return fail(PSK_EINVAL, "run ends of an asynchronously uploaded store are not positive and strictly increasing");
   }
   if (g.h_ctrl[CTRL_ERROR] != 0) {
     psk_store_release(res);
