@@ -798,7 +798,8 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
   hp.stagger_ns = g.stagger_ns;
 
   // ---- partition parameters: S * (m + 2k) <= kTileCap bounds the runs of one tile --------
-  int S = k <= 4 ? 256 : k <= 8 ? 128 : k <= 16 ? 64 : 32;
+  // (the rank-merge of the samples costs O(samples * k * log): keep S at 64 for wide steps)
+  int S = k <= 4 ? 256 : k <= 8 ? 128 : 64;
   while (S > 32 && total_runs / S < 2048) S >>= 1;
   int64_t max_samples = 0;
   for (int i = 0; i < k; ++i) max_samples += (hp.src[i].nruns + S - 1) / S;
