@@ -219,7 +219,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        lib.set_stream(torch.cuda.current_stream().cuda_stream)
 
     n_elems = int(N_ELEMS * args.scale)
     n_runs = int(N_RUNS * args.scale)
@@ -239,35 +238,70 @@ def main():
     def upload():
         return [lib.store_from_runs(pe.numpy(), pv.numpy()) for pe, pv in host]
 
-    def stitch(res):
-        """fuse_stores boundary rule across ranks (eval.hpp:581-588): drop my last run when
-        the next rank's first value is equal; global run offsets by exclusive scan."""
+    class _DevView:
+        """Zero-copy torch view of a device array owned by the library."""
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+
+    inflight = []      # (work, slot, result store kept alive)
+    stitched = []      # per finished step: host tensor [world, 3]
+
+    def stitch(res, step):
+        """fuse_stores boundary rule across ranks (eval.hpp:581-588): all-gather of every rank's
+        (first value, last value, run count); a rank drops its last run when the next rank starts
+        with an equal value, an exclusive scan of the counts gives global run offsets.  The
+        exchange is issued asynchronously on torch's stream (NCCL) straight from the result's
+        device arrays and is consumed two steps later, so it overlaps the next evaluations."""
         if dist is None:
-            return res.nruns
-        first, last, n = lib.store_boundary(res)
-        st_host[0], st_host[1], st_host[2] = first, last, n
-        st_mine.copy_(st_host, non_blocking=True)
-        dist.all_gather_into_tensor(st_all, st_mine)
-        st_all_host.copy_(st_all, non_blocking=True)
+            return
+        slot = step % 3
+        while inflight and inflight[0][1] == slot:
+            finish_one()
+        n = res.nruns
+        _, v_ptr = res.device_ptrs()
+        v = torch.as_tensor(_DevView(v_ptr, n), device="cuda")
+        mine = st_mine[slot]
+        mine[0:1].copy_(v[0:1])
+        mine[1:2].copy_(v[n - 1:n])
+        mine[2:3].fill_(n)
+        work = dist.all_gather_into_tensor(st_all[slot], mine, async_op=True)
+        inflight.append((work, slot, res))
+
+    def finish_one():
+        work, slot, _res = inflight.pop(0)
+        work.wait()
+        host = torch.empty(world * 3, dtype=torch.int64, pin_memory=True)
+        host.copy_(st_all[slot], non_blocking=True)
+        stitched.append(host)
+
+    def stitch_drain():
+        """-> global run count of the last step after applying the drop rule."""
+        while inflight:
+            finish_one()
+        if not stitched:
+            return None
         torch.cuda.current_stream().synchronize()
-        allv = st_all_host.view(world, 3)
+        allv = stitched[-1].view(world, 3)
         counts = allv[:, 2].clone()
         for r in range(world - 1):
             if allv[r, 1] == allv[r + 1, 0]:
                 counts[r] -= 1
+        stitched.clear()
         return int(counts.sum())
 
     if dist is not None:
-        st_host = torch.zeros(3, dtype=torch.int64, pin_memory=True)
-        st_mine = torch.zeros(3, dtype=torch.int64, device="cuda")
-        st_all = torch.zeros(world * 3, dtype=torch.int64, device="cuda")
-        st_all_host = torch.zeros(world * 3, dtype=torch.int64, pin_memory=True)
+        st_mine = [torch.zeros(3, dtype=torch.int64, device="cuda") for _ in range(3)]
+        st_all = [torch.zeros(world * 3, dtype=torch.int64, device="cuda") for _ in range(3)]
     resident = upload()
     srcs = [(s, []) for s in resident]
 
+    step_no = [0]
+
     def step_resident():
         res = lib.eval(srcs, prog, A.F32, A.EQ_BITWISE)
-        return res, stitch(res)
+        stitch(res, step_no[0])
+        step_no[0] += 1
+        return res
 
     def barrier():
         if dist is not None:
@@ -276,9 +310,10 @@ def main():
         lib.synchronize()
 
     for _ in range(args.warmup):
-        res, _ = step_resident()
+        res = step_resident()
     runs_out = res.nruns
     del res
+    stitch_drain()
 
     # ---- timed region: K resident steps, device events on the library stream -------------
     sampler = ClockSampler(local_rank)
@@ -290,8 +325,9 @@ def main():
     t0 = time.time()
     lib.timer_start()
     for _ in range(args.steps):
-        res, total_out = step_resident()
+        res = step_resident()
         del res
+    total_out = stitch_drain()            # every step's exchange has completed inside the region
     ms_total = lib.timer_stop()
     barrier()
     t1 = time.time()
