@@ -219,6 +219,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # one timeline for library kernels and NCCL: the stitch's send buffer is written by a
+        # library kernel and read by the all-gather without a host synchronisation
+        lib.set_stream(torch.cuda.current_stream().cuda_stream)
 
     n_elems = int(N_ELEMS * args.scale)
     n_runs = int(N_RUNS * args.scale)
@@ -238,11 +241,6 @@ def main():
     def upload():
         return [lib.store_from_runs(pe.numpy(), pv.numpy()) for pe, pv in host]
 
-    class _DevView:
-        """Zero-copy torch view of a device array owned by the library."""
-        def __init__(self, ptr, n):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
-
     inflight = []      # (work, slot, result store kept alive)
     stitched = []      # per finished step: host tensor [world, 3]
 
@@ -250,20 +248,15 @@ def main():
         """fuse_stores boundary rule across ranks (eval.hpp:581-588): all-gather of every rank's
         (first value, last value, run count); a rank drops its last run when the next rank starts
         with an equal value, an exclusive scan of the counts gives global run offsets.  The
-        exchange is issued asynchronously on torch's stream (NCCL) straight from the result's
-        device arrays and is consumed two steps later, so it overlaps the next evaluations."""
+        exchange is issued asynchronously (NCCL) from a send buffer that a library kernel fills
+        straight from the result's device arrays, and is consumed up to two steps later."""
         if dist is None:
             return
         slot = step % 3
         while inflight and inflight[0][1] == slot:
             finish_one()
-        n = res.nruns
-        _, v_ptr = res.device_ptrs()
-        v = torch.as_tensor(_DevView(v_ptr, n), device="cuda")
         mine = st_mine[slot]
-        mine[0:1].copy_(v[0:1])
-        mine[1:2].copy_(v[n - 1:n])
-        mine[2:3].fill_(n)
+        lib.store_boundary_device(res, mine.data_ptr())     # tiny kernel on the shared stream
         work = dist.all_gather_into_tensor(st_all[slot], mine, async_op=True)
         inflight.append((work, slot, res))
 

@@ -251,6 +251,9 @@ PSK_API psk_status psk_reduce(psk_store_t s, psk_reduce_op op, uint64_t* result_
  * A shard's first/last payloads and run count, for the stitch all-gather. */
 PSK_API psk_status psk_store_boundary(psk_store_t s, uint32_t* first_bits, uint32_t* last_bits,
                                       int64_t* nruns);
+/* Same triple written as 3 x int64 into DEVICE memory on the library stream (no host sync):
+ * the send buffer of the all-gather. */
+PSK_API psk_status psk_store_boundary_device(psk_store_t s, int64_t* d_out3);
 /* Sub-range [start, stop) of a store re-based to 0 (SimpleSource::split, eval.hpp:281-287). */
 PSK_API psk_status psk_store_slice(psk_store_t s, int32_t start, int32_t stop, psk_store_t* out);
 #endif /* !__CUDACC_RTC__ */

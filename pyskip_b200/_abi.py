@@ -109,7 +109,7 @@ _SYMBOLS = [
     "psk_store_to_dense_device", "psk_store_runs", "psk_store_nruns", "psk_store_span",
     "psk_store_dtype", "psk_store_device_ptrs", "psk_store_first_value", "psk_store_retain",
     "psk_store_release", "psk_eval", "psk_view_span", "psk_mask_nd", "psk_reduce",
-    "psk_store_boundary", "psk_store_slice",
+    "psk_store_boundary", "psk_store_boundary_device", "psk_store_slice",
 ]
 
 
@@ -199,6 +199,7 @@ class Lib:
         c.psk_store_runs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         c.psk_store_device_ptrs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         c.psk_store_first_value.argtypes = [C.c_void_p, C.c_void_p]
+        c.psk_store_boundary_device.argtypes = [C.c_void_p, C.c_void_p]
         c.psk_store_boundary.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         c.psk_store_slice.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         c.psk_eval.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -328,6 +329,9 @@ class Lib:
         a, b, n = C.c_uint32(), C.c_uint32(), C.c_int64()
         self._chk(self.c.psk_store_boundary(C.c_void_p(s.h), C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, n.value
+
+    def store_boundary_device(self, s: Store, d_out3: int):
+        self._chk(self.c.psk_store_boundary_device(C.c_void_p(s.h), C.c_void_p(d_out3)))
 
     # -- eval -------------------------------------------------------------------------
     def eval(self, sources, prog, out_dtype: int, eq: int = EQ_BITWISE) -> Store:

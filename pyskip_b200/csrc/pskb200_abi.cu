@@ -268,6 +268,15 @@ __global__ void k_validate_runs(const int32_t* ends, int32_t n, int32_t* flag) {
   }
 }
 
+// (first payload, last payload, run count) of a store, as int64, for the stitch all-gather
+__global__ void k_boundary(const uint32_t* vals, int64_t nruns, long long* out3) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    out3[0] = (long long)vals[0];
+    out3[1] = (long long)vals[nruns - 1];
+    out3[2] = (long long)nruns;
+  }
+}
+
 __global__ void k_fill_one(int32_t* ends, uint32_t* vals, int32_t span, uint32_t bits) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     ends[0] = span;
@@ -703,6 +712,13 @@ psk_status psk_store_boundary(psk_store_t s, uint32_t* first_bits, uint32_t* las
   *first_bits = (uint32_t)g.h_ctrl[0];
   *last_bits = (uint32_t)g.h_ctrl[1];
   *nruns = s->nruns;
+  return PSK_OK;
+}
+
+psk_status psk_store_boundary_device(psk_store_t s, int64_t* d_out3) {
+  NEED_INIT();
+  PSK_CHECK_ARG(s != nullptr && d_out3 != nullptr);
+  LAUNCH(k_boundary, 1, 32, 0, s->d_vals, (int64_t)s->nruns, reinterpret_cast<long long*>(d_out3));
   return PSK_OK;
 }
 
