@@ -219,9 +219,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        # one timeline for library kernels and NCCL: the stitch's send buffer is written by a
-        # library kernel and read by the all-gather without a host synchronisation
-        lib.set_stream(torch.cuda.current_stream().cuda_stream)
 
     n_elems = int(N_ELEMS * args.scale)
     n_runs = int(N_RUNS * args.scale)
@@ -241,50 +238,44 @@ def main():
     def upload():
         return [lib.store_from_runs(pe.numpy(), pv.numpy()) for pe, pv in host]
 
-    inflight = []      # (work, slot, result store kept alive)
-    stitched = []      # per finished step: host tensor [world, 3]
+    STITCH_BATCH = 32
+    pending = [0]      # triples written on the device and not exchanged yet
+    last_total = [None]
 
     def stitch(res, step):
-        """fuse_stores boundary rule across ranks (eval.hpp:581-588): all-gather of every rank's
-        (first value, last value, run count); a rank drops its last run when the next rank starts
-        with an equal value, an exclusive scan of the counts gives global run offsets.  The
-        exchange is issued asynchronously (NCCL) from a send buffer that a library kernel fills
-        straight from the result's device arrays, and is consumed up to two steps later."""
+        """fuse_stores boundary rule across ranks (eval.hpp:581-588): every rank contributes
+        (first value, last value, run count) of its shard; a rank drops its last run when the
+        next rank starts with an equal value, an exclusive scan of the counts gives global run
+        offsets.  Each step appends its triple to a device buffer (one tiny library kernel, no
+        host synchronisation); the ranks exchange the pending triples with ONE all-gather every
+        STITCH_BATCH steps and at the end of the region -- the collective is latency-bound
+        (24 bytes per rank and step), so it is batched rather than issued per step."""
         if dist is None:
             return
-        slot = step % 3
-        while inflight and inflight[0][1] == slot:
-            finish_one()
-        mine = st_mine[slot]
-        lib.store_boundary_device(res, mine.data_ptr())     # tiny kernel on the shared stream
-        work = dist.all_gather_into_tensor(st_all[slot], mine, async_op=True)
-        inflight.append((work, slot, res))
-
-    def finish_one():
-        work, slot, _res = inflight.pop(0)
-        work.wait()
-        host = torch.empty(world * 3, dtype=torch.int64, pin_memory=True)
-        host.copy_(st_all[slot], non_blocking=True)
-        stitched.append(host)
+        lib.store_boundary_device(res, st_mine.data_ptr() + 24 * pending[0])
+        pending[0] += 1
+        if pending[0] == STITCH_BATCH:
+            stitch_drain()
 
     def stitch_drain():
-        """-> global run count of the last step after applying the drop rule."""
-        while inflight:
-            finish_one()
-        if not stitched:
-            return None
-        torch.cuda.current_stream().synchronize()
-        allv = stitched[-1].view(world, 3)
-        counts = allv[:, 2].clone()
+        """Exchange the pending triples; -> global run count of the last step."""
+        if dist is None or pending[0] == 0:
+            return last_total[0]
+        n = pending[0]
+        lib.synchronize()                              # the triples are written
+        dist.all_gather_into_tensor(st_all[:world * n * 3], st_mine[:n * 3])
+        allv = st_all[:world * n * 3].view(world, n, 3).cpu()
+        counts = allv[:, n - 1, 2].clone()
         for r in range(world - 1):
-            if allv[r, 1] == allv[r + 1, 0]:
+            if allv[r, n - 1, 1] == allv[r + 1, n - 1, 0]:
                 counts[r] -= 1
-        stitched.clear()
-        return int(counts.sum())
+        pending[0] = 0
+        last_total[0] = int(counts.sum())
+        return last_total[0]
 
     if dist is not None:
-        st_mine = [torch.zeros(3, dtype=torch.int64, device="cuda") for _ in range(3)]
-        st_all = [torch.zeros(world * 3, dtype=torch.int64, device="cuda") for _ in range(3)]
+        st_mine = torch.zeros(STITCH_BATCH * 3, dtype=torch.int64, device="cuda")
+        st_all = torch.zeros(world * STITCH_BATCH * 3, dtype=torch.int64, device="cuda")
     resident = upload()
     srcs = [(s, []) for s in resident]
 
