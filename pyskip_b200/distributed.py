@@ -64,6 +64,9 @@ def _all_gather_i64(values):
     return out.cpu().numpy().reshape(size, len(values))
 
 
+_NP_OF = {int: np.int32, float: np.float32, bool: np.bool_}
+
+
 def _payload_bits(vals: np.ndarray) -> np.ndarray:
     if vals.dtype == np.float32:
         return vals.view(np.uint32).astype(np.int64)
@@ -106,24 +109,29 @@ class ShardedTensor:
     # ---- stitch: fuse_stores across ranks ----------------------------------------------
     def stitch(self, bitwise=True):
         """-> (runs this rank contributes, global index of its first run, global run count).
-        A rank's last run is dropped when the next shard starts with an equal value."""
+        A rank's last run is dropped when the next shard starts with an equal value.  Only the
+        first / last value and the run count of every shard are exchanged; nothing is copied
+        to the host."""
         src = self.local.eval() if bitwise else self.local
-        ends, vals = src.to_runs()
-        bits = _payload_bits(vals)
-        table = _all_gather_i64([int(bits[0]), int(bits[-1]), len(ends)])
+        n = len(src)
+        nruns = src.to_array().rle_length()
+        first = np.asarray([src[0]], dtype=_NP_OF[self.local.dtype])
+        last = np.asarray([src[n - 1]], dtype=_NP_OF[self.local.dtype])
+        table = _all_gather_i64([int(_payload_bits(first)[0]), int(_payload_bits(last)[0]), nruns])
         counts = table[:, 2].copy()
         for r in range(self.size - 1):
             if table[r, 1] == table[r + 1, 0]:
                 counts[r] -= 1          # eval.hpp:581-588
-        first = int(counts[:self.rank].sum())
-        keep = int(counts[self.rank])
-        return (ends[:keep], vals[:keep]), first, int(counts.sum())
+        self._evaluated = src
+        return int(counts[self.rank]), int(counts[:self.rank].sum()), int(counts.sum())
 
     def gather_global(self, bitwise=True):
         """All ranks -> the global (int64 ends, vals) run arrays (tests / small outputs)."""
         import torch
         dist = _dist()
-        (ends, vals), _, total = self.stitch(bitwise)
+        keep, _, total = self.stitch(bitwise)
+        ends, vals = self._evaluated.to_runs()
+        ends, vals = ends[:keep], vals[:keep]
         gl = ends.astype(np.int64) + self.offset
         if self.size == 1:
             return gl, vals

@@ -11,6 +11,9 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the native pieces are built in-tree (no-op when they are up to date)
+    from pyskip_b200 import build
+    build.build_all()
 
 
 @pytest.fixture(params=["sim", pytest.param("cuda", marks=pytest.mark.gpu)])

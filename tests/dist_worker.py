@@ -52,8 +52,8 @@ def main():
     ge, gv = out.gather_global()
     we, wv = O.eval_sources([(e, v, []) for e, v in srcs], lambda a, b, c: O.add(a, O.mul(b, c)))
     assert np.array_equal(ge, we.astype(np.int64)) and np.array_equal(gv, wv), "stitched eval differs"
-    (_, _), first, total = out.stitch()
-    assert total == len(we)
+    keep, first, total = out.stitch()
+    assert total == len(we) and 0 <= keep and first + keep <= total
 
     # ---- 2. reductions: local one-pass + all-reduce ------------------------------------------
     dense = O.to_dense(we, wv)
