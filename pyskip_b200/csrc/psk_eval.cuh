@@ -137,25 +137,57 @@ PSK_D int32_t sample_key(const DSource& s, int32_t j, int32_t S) {
   return mapped_end(s, s.a + off - 1);
 }
 
+// which source owns sample sid: last i with samp_off[i] <= sid (sources without samples
+// share their successor's offset and are skipped)
+PSK_D int sample_owner(const int32_t* s_off, int k, int32_t sid) {
+  int l = 0, h = k - 1;
+  while (l < h) {
+    const int mid = (l + h + 1) >> 1;
+    if (s_off[mid] <= sid) l = mid; else h = mid - 1;
+  }
+  return l;
+}
+
 // ---------------------------------------------------------------------------------------
-// k_sample_rank: merged[rank] = key, where rank orders all samples by (key, source, index).
-__global__ void k_sample_rank(DPlan* p) {
-  int32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
+// k_sample_keys: samp_keys[sid] = mapped end of sample sid.  The view chain of a source is
+// evaluated once per sample here, never inside the ranking searches.
+__global__ void k_sample_keys(DPlan* p) {
+  __shared__ int32_t s_off[PSK_MAX_SOURCES];
+  const int k = p->k;
+  if ((int)threadIdx.x < k) s_off[threadIdx.x] = p->src[threadIdx.x].samp_off;
+  __syncthreads();
+  const int32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
   if (sid >= p->total_samples) return;
-  const int k = p->k, S = p->S;
-  int i = 0;
-  while (i + 1 < k && p->src[i + 1].samp_off <= sid) ++i;
-  const int32_t j = sid - p->src[i].samp_off;
-  const int32_t key = sample_key(p->src[i], j, S);
-  int32_t rank = j;
+  const int i = sample_owner(s_off, k, sid);
+  p->samp_keys[sid] = sample_key(p->src[i], sid - s_off[i], p->S);
+}
+
+// ---------------------------------------------------------------------------------------
+// k_sample_rank: merged[rank] = key, where rank orders all samples by (key, source, index):
+// own index + one binary search over the sample keys of every other source.
+__global__ void k_sample_rank(DPlan* p) {
+  __shared__ int32_t s_off[PSK_MAX_SOURCES];
+  __shared__ int32_t s_ns[PSK_MAX_SOURCES];
+  const int k = p->k;
+  if ((int)threadIdx.x < k) {
+    s_off[threadIdx.x] = p->src[threadIdx.x].samp_off;
+    s_ns[threadIdx.x] = p->src[threadIdx.x].ns;
+  }
+  __syncthreads();
+  const int32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sid >= p->total_samples) return;
+  const int32_t* const keys = p->samp_keys;
+  const int i = sample_owner(s_off, k, sid);
+  const int32_t key = keys[sid];
+  int32_t rank = sid - s_off[i];
   for (int q = 0; q < k; ++q) {
     if (q == i) continue;
-    const DSource& s = p->src[q];
-    int32_t lo = 0, hi = s.ns;
+    const int32_t* const kq = keys + s_off[q];
+    int32_t lo = 0, hi = s_ns[q];
     while (lo < hi) {
-      int32_t mid = lo + ((hi - lo) >> 1);
-      int32_t kq = sample_key(s, mid, S);
-      bool before = (q < i) ? (kq <= key) : (kq < key);
+      const int32_t mid = lo + ((hi - lo) >> 1);
+      const int32_t v = kq[mid];
+      const bool before = (q < i) ? (v <= key) : (v < key);
       if (before) lo = mid + 1; else hi = mid;
     }
     rank += lo;

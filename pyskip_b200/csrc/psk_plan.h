@@ -53,6 +53,7 @@ struct DPlan {
   int32_t any_views;
   int32_t stagger_ns;  // start delay per CTA index: de-phases the persistent CTAs
   // scratch + output (device pointers)
+  int32_t* samp_keys;              // [max_samples] sample keys, source by source
   int32_t* merged;                 // [max_samples] sorted sample keys
   int32_t* bounds;                 // [(max_tiles+1) * k] per-tile raw index bounds
   int32_t* tile_hi;                // [max_tiles] inclusive upper coordinate of each tile

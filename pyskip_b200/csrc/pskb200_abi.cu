@@ -846,12 +846,13 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
     hp.n_tiles = 0;
   }
 
-  // ---- scratch: [tile_state | ctrl | merged | bounds | tile_hi | plan] --------------------
+  // ---- scratch: [tile_state | ctrl | merged | samp_keys | bounds | tile_hi | plan] ---------
   size_t o_state = 0;
   size_t o_phase = o_state + (size_t)max_tiles * 8;
   size_t o_ctrl = o_phase + 8 * 8;
   size_t o_merged = o_ctrl + CTRL_WORDS * 4;
-  size_t o_bounds = o_merged + (size_t)max_samples * 4;
+  size_t o_keys = o_merged + (size_t)max_samples * 4;
+  size_t o_bounds = o_keys + (size_t)max_samples * 4;
   size_t o_hi = o_bounds + (size_t)(max_tiles + 1) * k * 4;
   size_t o_plan = (o_hi + (size_t)max_tiles * 4 + 15) & ~(size_t)15;
   const size_t plan_bytes = offsetof(DPlan, src) + sizeof(DSource) * (size_t)k;
@@ -876,6 +877,7 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
   }
 #endif
   hp.merged = reinterpret_cast<int32_t*>(scratch + o_merged);
+  hp.samp_keys = reinterpret_cast<int32_t*>(scratch + o_keys);
   hp.bounds = reinterpret_cast<int32_t*>(scratch + o_bounds);
   hp.tile_hi = reinterpret_cast<int32_t*>(scratch + o_hi);
   hp.out_ends = res->d_ends;
@@ -887,6 +889,7 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_plan, &hp, plan_bytes, cudaMemcpyHostToDevice, g.stream);
   if (e == cudaSuccess) {
     if (any_views) LAUNCH(k_prepare, 1, 32, 0, d_plan);
+    LAUNCH(k_sample_keys, (unsigned)((max_samples + 255) / 256), 256, 0, d_plan);
     LAUNCH(k_sample_rank, (unsigned)((max_samples + 255) / 256), 256, 0, d_plan);
     LAUNCH(k_tile_bounds, (unsigned)(((max_tiles + 1) * k + 255) / 256), 256, 0, d_plan);
     // persistent grid: as many CTAs as stay resident (shared memory / thread limits)

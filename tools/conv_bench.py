@@ -16,7 +16,25 @@ from pyskip_b200 import _abi, _pyskip_b200_ext as E
 from test_full_size import _terrain
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-lib = _abi.lib()
+PHASE = os.environ.get("PSK_CONV_PHASE") == "1"
+if PHASE:
+    # per-phase cycle counters of the merge kernel: a -DPSK_PHASE_TIMING build bound in place of the product
+    import ctypes as C
+    import subprocess
+    from pyskip_b200 import build as B
+    vpath = os.path.join(ROOT, "_variants", "libpskb200_convphase.so")
+    os.makedirs(os.path.dirname(vpath), exist_ok=True)
+    if not os.path.exists(vpath):
+        B.gen_jit_embed()
+        subprocess.check_call([B.nvcc_path()] + B.NVCC_FLAGS + B.nvrtc_define() + ["-DPSK_PHASE_TIMING", "-I" + B.CSRC,
+                              os.path.join(B.CSRC, "pskb200_abi.cu"), os.path.join(B.CSRC, "psk_jit.cpp"),
+                              "-o", vpath, "-ldl"])
+    if os.environ.get("PSK_BUILD_ONLY") == "1":
+        sys.exit(0)
+    E._bind_backend(vpath, True)
+    lib = _abi.Lib(vpath)
+else:
+    lib = _abi.lib()
 vol = _terrain(n)
 ker = np.random.default_rng(3001).integers(0, 8, size=(3, 3, 3)).astype(np.int32)
 t = ps.Tensor.from_numpy(vol).eval()
@@ -27,6 +45,9 @@ for _ in range(2):
 r_out = out.rle_length()
 E.synchronize()
 lib.profile(True)
+if PHASE:
+    buf = (C.c_ulonglong * 8)()
+    lib.c.psk_phase_read(buf, 1)
 reps = 5
 times = []
 for _ in range(reps):
@@ -42,6 +63,14 @@ print(f"conv_3d {n}^3: runs in {r_in} ({r_in / vol.size * 100:.2f} %), runs out 
       f"merge_eval kernels {ms / reps:.3f} ms per conv over {nev // reps} launches; "
       f"algorithmic {8 * (r_in + r_out) / 1e6:.1f} MB -> {8 * (r_in + r_out) / (ms / reps * 1e-3) / 1e9:.0f} GB/s "
       f"of the merge kernels' time; jit launches {lib.jit_launch_count()}")
+if PHASE:
+    lib.c.psk_phase_read(buf, 1)
+    names = ["ticket+desc", "staging", "thread search", "merge (thread 0)", "wait slowest+scan", "lookback+write prev",
+             "compaction", "-"]
+    tot = sum(buf) or 1
+    for nm, v in zip(names, buf):
+        print(f"  {nm:22s} {100.0 * v / tot:6.2f} %")
+    sys.exit(0)
 try:
     sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
     import _pyskip_cpp_ext as R

@@ -28,7 +28,7 @@ if args.cap:
     defs.append(f"-DPSK_TILE_CAP={args.cap}")
 if args.lbwarp:
     defs.append("-DPSK_LOOKBACK_WARP")
-out = os.path.join(ROOT, "gpurun_out", f"libpskb200_phase_{args.threads}_{args.cap}_{int(args.no_phase)}_{int(args.lbwarp)}.so")
+out = os.path.join(ROOT, "_variants", f"libpskb200_phase_{args.threads}_{args.cap}_{int(args.no_phase)}_{int(args.lbwarp)}.so")
 os.makedirs(os.path.dirname(out), exist_ok=True)
 if args.build_only or not os.path.exists(out):
     B.gen_jit_embed()
@@ -76,7 +76,7 @@ if not args.no_phase:
         print("tile start spread: first", int(t0[:, 0].min() - t0[:, 0].min()), "last", int(t0[:, 6].max() - t0[:, 0].min()))
 names = ["ticket+desc", "staging", "thread search", "merge (thread 0)", "wait slowest+scan", "lookback+compact",
          "global write", "-"]
-print(f"threads {args.threads or 512} cap {args.cap or 6144} lbwarp {args.lbwarp}")
+print(f"threads {args.threads or 512} cap {args.cap or 8192} lbwarp {args.lbwarp}")
 print(f"merge_eval avg {ms / ne:.3f} ms; runs in {ri // ne} out {ro // ne}; jit launches {lib.jit_launch_count()}")
 for nm, c in zip(names, buf):
     print(f"  {nm:22s} {c / max(tot, 1) * 100:6.2f} %   {c / N / 296:12.0f} cycles per CTA per eval")
