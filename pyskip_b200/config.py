@@ -1,7 +1,9 @@
 """Configuration scopes (src/pyskip/config.py:8-58) over the extension's global config map.
 
 Keys understood by the GPU backend: ``flush_tree_size_threshold`` (expression size above
-which an array is evaluated eagerly; reference array.hpp:210).  ``accelerated_eval``,
+which an array is evaluated eagerly; reference array.hpp:210) and ``gpu_eval_max_sources``
+(sources merged per kernel launch, 2..30, default 8: wider expressions run as a chain of
+launches because the k-way merge step costs O(k) per run).  ``accelerated_eval``,
 ``parallelize_threshold`` and ``parallelize_parts`` are accepted for compatibility and have
 no effect (they select CPU code paths; results never depended on them)."""
 from contextlib import contextmanager

@@ -29,6 +29,7 @@
 namespace psk_host {
 
 constexpr int kMaxWidth = 30;    // sources per launch (PSK_MAX_SOURCES = 32)
+constexpr int kDefaultWidth = 8;   // measured optimum on the 27-tap voxel convolution (profiles/r1_summary.md)
 constexpr int kMaxProgram = 160; // nodes per launch  (PSK_MAX_PROGRAM = 192)
 constexpr int kMaxDepth = 36;    // stack depth       (kMaxStack = 40 in the kernels)
 
@@ -208,6 +209,9 @@ class Planner {
   }
 
   std::unordered_map<const Expr*, bool> feasible_;
+  // sources per launch: the merge step costs O(k) per run, so a wide expression is cheaper as
+  // a short chain of narrower launches (config key "gpu_eval_max_sources", 2..30)
+  int max_width_ = (int)std::min<int64_t>(kMaxWidth, std::max<int64_t>(2, config_get_int("gpu_eval_max_sources", kDefaultWidth)));
 
   // Materialise sub-expressions until `e` fits one launch.
   void make_feasible(const Expr* e0) {
@@ -224,7 +228,7 @@ class Planner {
       const Expr* r = resolve(d);
       if (r->kind != Expr::STORE && parents_[d] > 1 && width(d) >= 2) replace_with_store(d, run_sub(d));
     }
-    while (width(e) > kMaxWidth || prog_len(e) > kMaxProgram || depth(e) > kMaxDepth ||
+    while (width(e) > max_width_ || prog_len(e) > kMaxProgram || depth(e) > kMaxDepth ||
            chain_len(e) > PSK_MAX_VIEWS) {
       // materialise the heaviest child that is not already a store
       int best = -1, best_w = -1;

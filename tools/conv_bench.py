@@ -35,6 +35,8 @@ if PHASE:
     lib = _abi.Lib(vpath)
 else:
     lib = _abi.lib()
+if os.environ.get("PSK_CONV_WIDTH"):
+    ps.config.set_value("gpu_eval_max_sources", int(os.environ["PSK_CONV_WIDTH"]))
 vol = _terrain(n)
 ker = np.random.default_rng(3001).integers(0, 8, size=(3, 3, 3)).astype(np.int32)
 t = ps.Tensor.from_numpy(vol).eval()
