@@ -96,29 +96,56 @@ PSK_D int32_t lb_mapped(const DSource& s, int32_t lo, int32_t hi, int32_t key) {
   return lo;
 }
 
+// Warp-cooperative form of the two searches above: 32 probes per round, so a source of 2^21
+// runs takes 5 rounds of (load + view chain) instead of 21 dependent ones.
+// strict = true: first index whose mapped end is > key; false: >= key.
+PSK_D int32_t warp_bound_mapped(const DSource& s, int32_t lo, int32_t hi, int32_t key, bool strict) {
+  const int lane = threadIdx.x & 31;
+  while (hi - lo > 32) {
+    // probes at strictly increasing indices inside [lo, hi)
+    const int32_t idx = lo + (int32_t)(((long long)(hi - lo) * (lane + 1)) / 33);
+    const int32_t me = mapped_end(s, idx);
+    const bool before = strict ? (me <= key) : (me < key);
+    const int nb = __popc(__ballot_sync(0xffffffffu, before));  // a prefix of the lanes
+    const int32_t last_before = __shfl_sync(0xffffffffu, idx, nb > 0 ? nb - 1 : 0);
+    const int32_t first_after = __shfl_sync(0xffffffffu, idx, nb < 32 ? nb : 31);
+    if (nb < 32) hi = first_after;
+    if (nb > 0) lo = last_before + 1;
+  }
+  const int32_t idx = lo + lane;
+  bool before = false;
+  if (idx < hi) {
+    const int32_t me = mapped_end(s, idx);
+    before = strict ? (me <= key) : (me < key);
+  }
+  return lo + __popc(__ballot_sync(0xffffffffu, before));
+}
+
 // ---------------------------------------------------------------------------------------
-// k_prepare: one thread per source.  [a, e) = runs whose mapped end is in (0, span], cut
+// k_prepare: one warp per source.  [a, e) = runs whose mapped end is in (0, span], cut
 // after the first run that reaches span (everything later is a zero-length mapped run).
 __global__ void k_prepare(DPlan* p) {
   __shared__ int32_t s_ns[PSK_MAX_SOURCES];
-  int i = threadIdx.x;
-  int k = p->k;
+  const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = p->k;
   if (i < k) {
     DSource& s = p->src[i];
     int32_t a = 0, e = s.nruns;
     if (s.nviews) {
-      a = ub_mapped(s, 0, s.nruns, 0);
-      e = lb_mapped(s, a, s.nruns, p->span) + 1;
+      a = warp_bound_mapped(s, 0, s.nruns, 0, true);
+      e = warp_bound_mapped(s, a, s.nruns, p->span, false) + 1;
       if (e > s.nruns) e = s.nruns;
     }
-    s.a = a;
-    s.e = e;
-    int32_t n = e - a;
-    s.ns = (n + p->S - 1) / p->S;
-    s_ns[i] = s.ns;
+    if (lane == 0) {
+      s.a = a;
+      s.e = e;
+      const int32_t n = e - a;
+      s.ns = (n + p->S - 1) / p->S;
+      s_ns[i] = s.ns;
+    }
   }
   __syncthreads();
-  if (i == 0) {
+  if (threadIdx.x == 0) {
     int32_t off = 0;
     for (int q = 0; q < k; ++q) {
       p->src[q].samp_off = off;
@@ -196,7 +223,9 @@ __global__ void k_sample_rank(DPlan* p) {
 }
 
 // ---------------------------------------------------------------------------------------
-// k_tile_bounds: bounds[t][i] = first run of source i whose mapped end is > hi(t-1).
+// k_tile_bounds: bounds[t][i] = first run of source i whose mapped end is > hi(t-1).  The
+// source's own sample keys narrow the search to one sample interval (<= S runs) before any
+// run end is loaded or mapped.
 __global__ void k_tile_bounds(DPlan* p) {
   int32_t id = blockIdx.x * blockDim.x + threadIdx.x;
   const int k = p->k, nt = p->n_tiles, m = p->m;
@@ -209,7 +238,22 @@ __global__ void k_tile_bounds(DPlan* p) {
   } else if (t == nt) {
     b = s.e;
   } else {
-    b = ub_mapped(s, s.a, s.e, p->merged[t * m - 1]);
+    const int32_t key = p->merged[t * m - 1];
+    const int32_t* const kq = p->samp_keys + s.samp_off;
+    int32_t lo = 0, hi = s.ns;  // first sample whose key is > key
+    while (lo < hi) {
+      const int32_t mid = lo + ((hi - lo) >> 1);
+      if (kq[mid] <= key) lo = mid + 1; else hi = mid;
+    }
+    if (lo == s.ns) {
+      b = s.e;  // the last sample is the source's last run
+    } else {
+      // sample j is run a + min((j + 1) S, n) - 1: every run up to sample lo - 1 is <= key,
+      // the run of sample lo is > key
+      const int32_t n = s.e - s.a;
+      const int32_t r = s.a + imin((lo + 1) * p->S, n) - 1;
+      b = ub_mapped(s, s.a + lo * p->S, r, key);
+    }
   }
   p->bounds[t * k + i] = b;
   if (i == 0 && t > 0) p->tile_hi[t - 1] = (t == nt) ? p->span : p->merged[t * m - 1];
@@ -394,20 +438,20 @@ PSK_D void store_tile_desc(const DescRegs& r, TileDesc* d, int k) {
   }
 }
 
-// Where the runs of a tile go in the shared tile buffer: sources without a view occupy the
-// flat slots [0, flat_total) back to back (slice + one look-ahead run each); sources with a
-// view are appended behind them by the staging pass that maps and filters them.
+// Where the RAW runs of a tile go in the shared tile buffer: the sources occupy the flat
+// slots [0, flat_total) back to back (slice + one look-ahead run each).  With views the
+// staging pass then maps the ends and squeezes out zero-length mapped runs in place.
 struct TileLayout {
   int32_t off[PSK_MAX_SOURCES + 1];
   int32_t len[PSK_MAX_SOURCES];  // staged runs (excl. look-ahead)
   int32_t flat_total;
 };
 
-// one warp: layout of the view-less sources of tile d
+// one warp: layout of tile d
 PSK_D void compute_layout(const TileDesc& d, const SrcDesc* src, int k, TileLayout* L) {
   const int lane = threadIdx.x & 31;
   int32_t len = 0;
-  if (lane < k && src[lane].nviews == 0) len = d.b1[lane] - d.b0[lane] + 1;  // + look-ahead
+  if (lane < k) len = d.b1[lane] - d.b0[lane] + 1;  // + look-ahead
   int32_t inc = len;
 #pragma unroll
   for (int dd = 1; dd < 32; dd <<= 1) {
@@ -421,7 +465,25 @@ PSK_D void compute_layout(const TileDesc& d, const SrcDesc* src, int k, TileLayo
   if (lane == 31) L->flat_total = inc;
 }
 
-// all threads: issue the global loads of the tile's view-less sources into registers (flat
+// which source owns flat slot j: last i with off[i] <= j (every source has >= 1 slot)
+template <int K>
+PSK_D int slot_owner(const int32_t* off, int k, int32_t j) {
+  int i = 0;
+  if (K <= 8) {
+#pragma unroll
+    for (int q = 1; q < K; ++q) i += (q < k && off[q] <= j) ? 1 : 0;
+  } else {
+    int l = 0, h = k - 1;
+    while (l < h) {
+      const int mid = (l + h + 1) >> 1;
+      if (off[mid] <= j) l = mid; else h = mid - 1;
+    }
+    i = l;
+  }
+  return i;
+}
+
+// all threads: issue the global loads of the tile's raw runs into registers (flat
 // slot j = tid + u*T).  Nothing waits on them here; they are stored to shared memory one
 // tile later, so the HBM latency overlaps the merge of the tile in front.
 template <int K, int T, int NB>
@@ -433,20 +495,7 @@ PSK_D void issue_tile_loads(const TileDesc& d, const TileLayout& L, const SrcDes
     const int32_t j = (int32_t)threadIdx.x + u * T;
     pr[u] = make_int2(kSentinel, 0);  // no run beyond the tile: sentinel look-ahead
     if (j < used && used <= limit) {
-      // which source owns flat slot j: last i with off[i] <= j (view sources have zero slots
-      // here and are never the last such i)
-      int i = 0;
-      if (K <= 8) {
-#pragma unroll
-        for (int q = 1; q < K; ++q) i += (q < k && L.off[q] <= j) ? 1 : 0;
-      } else {
-        int l = 0, h = k - 1;
-        while (l < h) {
-          int mid = (l + h + 1) >> 1;
-          if (L.off[mid] <= j) l = mid; else h = mid - 1;
-        }
-        i = l;
-      }
+      const int i = slot_owner<K>(L.off, k, j);
       const int32_t r = j - L.off[i];
       const int32_t idx = d.b0[i] + r;
       if (r < L.len[i] || idx < src[i].e) {
@@ -459,7 +508,9 @@ PSK_D void issue_tile_loads(const TileDesc& d, const TileLayout& L, const SrcDes
 
 // TYPED_FLOAT: compaction compares float values with operator== (PSK_EQ_TYPED on F32)
 // instead of the 32-bit payloads.
-template <int K, bool TYPED_FLOAT, typename Eval>
+// VIEWS: 1 = some source has a view, 0 = none (the staging pass is compiled out), -1 = ask
+// the plan at run time (the interpreter kernels).
+template <int K, bool TYPED_FLOAT, int VIEWS, typename Eval>
 PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
   constexpr int T = kTileThreads;
   constexpr int CAP = kTileCap;
@@ -475,7 +526,8 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
   __shared__ SrcDesc s_src[PSK_MAX_SOURCES];
   __shared__ int32_t s_warp[T / 32 + 2];
   __shared__ int32_t s_lbhas[T / 32];
-  __shared__ int32_t s_carry;
+  __shared__ int32_t s_newoff[PSK_MAX_SOURCES];  // with views: slot layout after the squeeze
+  __shared__ int32_t s_newend[PSK_MAX_SOURCES];
 
   constexpr int PEND = IN_N + CAP;        // third region: compacted spans awaiting their offset
   int32_t pend_tile = -1, pend_total = 0;
@@ -485,7 +537,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
   const int tid = threadIdx.x;
   const int k = p->k;
   constexpr bool typed_float = TYPED_FLOAT;
-  const bool any_views = p->any_views != 0;
+  const bool any_views = VIEWS < 0 ? (p->any_views != 0) : (VIEWS != 0);
   const int32_t span = p->span;
   const int32_t n_tiles = p->n_tiles;
 
@@ -529,7 +581,16 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
 #pragma unroll
       for (int u = 0; u < NB; ++u) {
         const int32_t j = tid + u * T;
-        if (j < used) sm.st(j, pr[u].x, pr[u].y);
+        if (j < used) {
+          int32_t x = pr[u].x;
+          if (any_views) {
+            // raw end -> coordinate of the expression through the source's view chain
+            const int i = slot_owner<K>(s_off, k, j);
+            const int nv = s_src[i].nviews;
+            if (nv) x = (d.b0[i] + (j - s_off[i]) < s_src[i].e) ? map_chain(p->src[i].v, nv, x) : kSentinel;
+          }
+          sm.st(j, x, pr[u].y);
+        }
       }
     }
     DescRegs fetched;
@@ -540,47 +601,66 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
       fetched = fetch_tile_desc(p, k, n_tiles);
     }
     PSK_PHASE(0);
-    // ---- sources with a view: mapped ends, zero-length mapped runs dropped ---------------
+    // ---- with views: squeeze out the zero-length mapped runs (mapped end not beyond its
+    //      predecessor's) in place.  Every thread takes nb consecutive slots (nb odd: the
+    //      strided shared accesses hit distinct banks); one block scan gives the new slots. --
     if (any_views && !fail) {
-      for (int i = 0; i < k; ++i) {
-        if (s_src[i].nviews == 0) continue;  // uniform branch
-        const DSource& s = p->src[i];
-        const int32_t b0 = d.b0[i], b1 = d.b1[i];
-        const int32_t off = used;
-        int32_t kept = 0;
-        __syncthreads();
-        if (tid == 0) s_carry = lo;
-        for (int32_t base = b0; base < b1; base += T) {
-          __syncthreads();
-          const int32_t idx = base + tid;
-          const bool valid = idx < b1;
-          const int32_t me = valid ? map_chain(s.v, s.nviews, s.ends[idx]) : kSentinel;
-          int32_t* s_last = s_warp;  // [T/32] last mapped end of each warp
-          int32_t pm = __shfl_up_sync(0xffffffffu, me, 1);
-          if ((tid & 31) == 31) s_last[tid >> 5] = me;
-          __syncthreads();
-          if ((tid & 31) == 0) pm = (tid == 0) ? s_carry : s_last[(tid >> 5) - 1];
-          const bool keep = valid && me > pm;
-          __syncthreads();  // s_last consumed before the scan reuses s_warp
-          int32_t tot;
-          const int32_t pos = block_exclusive_scan<T>(keep ? 1 : 0, s_warp, &tot);
-          if (keep && off + kept + pos < IN_N) sm.st(off + kept + pos, me, (int32_t)s.vals[idx]);
-          kept += tot;
-          const int32_t last_valid = (b1 - base < T ? b1 - base : T) - 1;
-          if (tid == last_valid) s_carry = me;
+      constexpr int NBO = NB | 1;
+      __syncthreads();
+      const int32_t nb = ((used + T - 1) / T) | 1;
+      const int32_t j0 = tid * nb;
+      int2 run_[NBO];
+      int32_t prev = (j0 > 0 && j0 <= used) ? sm.ldx(j0 - 1) : 0;
+#pragma unroll
+      for (int u = 0; u < NBO; ++u)
+        run_[u] = (u < nb && j0 + u < used) ? sm.ld(j0 + u) : make_int2(-1, 0);
+      int i = slot_owner<K>(s_off, k, imin(j0, used - 1));
+      int32_t nxt = (i + 1 < k) ? s_off[i + 1] : used;  // first slot of the next source
+      int32_t kept = 0;
+#pragma unroll
+      for (int u = 0; u < NBO; ++u) {
+        const int32_t j = j0 + u;
+        if (u < nb && j < used) {
+          if (j == nxt) {
+            ++i;
+            nxt = (i + 1 < k) ? s_off[i + 1] : used;
+          }
+          const int32_t me = run_[u].x;
+          // a source's first run is measured against the tile's lower bound; its look-ahead
+          // run (last slot) always stays
+          const int32_t before = (j == s_off[i]) ? lo : prev;
+          const bool keep = s_src[i].nviews == 0 || j == nxt - 1 || me > before;
+          prev = me;
+          if (keep) ++kept; else run_[u].x = -1;
         }
-        if (off + kept + 1 > IN_N) {
-          fail = true;  // uniform: every thread sees the same kept
-          break;
-        }
-        if (tid == 0) {
-          if (b1 < s.e) sm.st(off + kept, mapped_end(s, b1), (int32_t)s.vals[b1]);
-          else sm.st(off + kept, kSentinel, 0);
-          s_off[i] = off;
-          s_len[i] = kept;
-        }
-        used = off + kept + 1;
       }
+      int32_t total;
+      int32_t pos = block_exclusive_scan<T>(kept, s_warp, &total);
+      // (the scan's barriers also order every read above before the writes below)
+      i = slot_owner<K>(s_off, k, imin(j0, used - 1));
+      nxt = (i + 1 < k) ? s_off[i + 1] : used;
+#pragma unroll
+      for (int u = 0; u < NBO; ++u) {
+        const int32_t j = j0 + u;
+        if (u < nb && j < used) {
+          if (j == nxt) {
+            ++i;
+            nxt = (i + 1 < k) ? s_off[i + 1] : used;
+          }
+          if (j == s_off[i]) s_newoff[i] = pos;
+          if (j == nxt - 1) s_newend[i] = pos;  // the look-ahead run is always kept
+          if (run_[u].x >= 0) {
+            sm.st(pos, run_[u].x, run_[u].y);
+            ++pos;
+          }
+        }
+      }
+      __syncthreads();
+      if (tid < k) {
+        s_off[tid] = s_newoff[tid];
+        s_len[tid] = s_newend[tid] - s_newoff[tid];
+      }
+      used = total;
     }
     __syncthreads();
     PSK_PHASE(1);  // staging
@@ -718,8 +798,8 @@ __global__ void __launch_bounds__(kTileThreads, kCtasPerSm) k_merge_eval_interp(
   for (int i = threadIdx.x; i < p->nprog; i += blockDim.x) s_prog[i] = p->prog[i];
   __syncthreads();
   InterpEval ev{s_prog, p->nprog};
-  if (p->eq != 0) merge_eval_tile_loop<K, true>(p, ev);
-  else merge_eval_tile_loop<K, false>(p, ev);
+  if (p->eq != 0) merge_eval_tile_loop<K, true, -1>(p, ev);
+  else merge_eval_tile_loop<K, false, -1>(p, ev);
 }
 
 

@@ -131,7 +131,7 @@ bool load_api() {
 
 // postfix program -> straight-line SSA over apply_unary / apply_binary with literal op-codes
 // (the switch inside them folds away at compile time)
-std::string gen_source(int K, bool typed_float, int nprog, const psk_node* prog) {
+std::string gen_source(int K, bool typed_float, bool views, int nprog, const psk_node* prog) {
   std::string body;
   std::vector<int> st;
   int next = 0;
@@ -181,7 +181,7 @@ std::string gen_source(int K, bool typed_float, int nprog, const psk_node* prog)
   src += body;
   src += "  }\n};\n}  // namespace psk\n";
   snprintf(buf, sizeof buf,
-           "  psk::merge_eval_tile_loop<%d, %s>(p, ev);\n}\n", K, typed_float ? "true" : "false");
+           "  psk::merge_eval_tile_loop<%d, %s, %d>(p, ev);\n}\n", K, typed_float ? "true" : "false", views ? 1 : 0);
   src += "extern \"C\" __global__ void __launch_bounds__(psk::kTileThreads, psk::kCtasPerSm) psk_jit_merge_eval(psk::DPlan* p) {\n"
          "  psk::JitEval ev;\n";
   src += inits;
@@ -189,11 +189,12 @@ std::string gen_source(int K, bool typed_float, int nprog, const psk_node* prog)
   return src;
 }
 
-std::string cache_key(int K, bool typed_float, int nprog, const psk_node* prog) {
+std::string cache_key(int K, bool typed_float, bool views, int nprog, const psk_node* prog) {
   std::string key;
   key.reserve(nprog * 3 + 8);
   key += (char)K;
   key += typed_float ? 'T' : 'B';
+  key += views ? 'V' : 'F';
   for (int i = 0; i < nprog; ++i) {
     key += (char)prog[i].op;
     key += (char)(prog[i].op == PSK_OP_SRC ? prog[i].arg : 0);
@@ -201,9 +202,9 @@ std::string cache_key(int K, bool typed_float, int nprog, const psk_node* prog) 
   return key;
 }
 
-bool compile_cubin(int K, bool typed_float, int nprog, const psk_node* prog, std::vector<char>* cubin,
+bool compile_cubin(int K, bool typed_float, bool views, int nprog, const psk_node* prog, std::vector<char>* cubin,
                    std::string* why) {
-  const std::string src = gen_source(K, typed_float, nprog, prog);
+  const std::string src = gen_source(K, typed_float, views, nprog, prog);
   nvrtcProgram np = nullptr;
   int r = g_api.nvrtcCreateProgram(&np, src.c_str(), "psk_jit_merge_eval.cu", kJitNumHeaders, kJitHeaderSources,
                                    kJitHeaderNames);
@@ -255,9 +256,9 @@ bool compile_cubin(int K, bool typed_float, int nprog, const psk_node* prog, std
   return true;
 }
 
-JitKernel* compile(int K, bool typed_float, int nprog, const psk_node* prog, std::string* why) {
+JitKernel* compile(int K, bool typed_float, bool views, int nprog, const psk_node* prog, std::string* why) {
   std::vector<char> cubin;
-  if (!compile_cubin(K, typed_float, nprog, prog, &cubin, why)) return nullptr;
+  if (!compile_cubin(K, typed_float, views, nprog, prog, &cubin, why)) return nullptr;
   void* mod = nullptr;
   int r = g_api.cuModuleLoadData(&mod, cubin.data());
   if (r != 0) {
@@ -277,20 +278,20 @@ JitKernel* compile(int K, bool typed_float, int nprog, const psk_node* prog, std
 
 }  // namespace
 
-const JitKernel* jit_get_merge_eval(int K, bool typed_float, int nprog, const psk_node* prog, const char** why) {
+const JitKernel* jit_get_merge_eval(int K, bool typed_float, bool views, int nprog, const psk_node* prog, const char** why) {
   std::lock_guard<std::mutex> l(g_mu);
   static std::string s_why;
   if (!load_api()) {
     if (why) *why = g_api.why.c_str();
     return nullptr;
   }
-  const std::string key = cache_key(K, typed_float, nprog, prog);
+  const std::string key = cache_key(K, typed_float, views, nprog, prog);
   auto it = g_cache.find(key);
   if (it != g_cache.end()) {
     if (!it->second && why) *why = "previous compilation of this program failed";
     return it->second;
   }
-  JitKernel* k = compile(K, typed_float, nprog, prog, &s_why);
+  JitKernel* k = compile(K, typed_float, views, nprog, prog, &s_why);
   if (k) {
     ++g_compiled;
   } else {
@@ -321,7 +322,8 @@ int jit_compile_check(int K, bool typed_float, int nprog, const psk_node* prog, 
   std::lock_guard<std::mutex> l(g_mu);
   std::string why;
   std::vector<char> cubin;
-  bool ok = load_nvrtc() && compile_cubin(K, typed_float, nprog, prog, &cubin, &why);
+  bool ok = load_nvrtc() && compile_cubin(K, typed_float, false, nprog, prog, &cubin, &why) &&
+            compile_cubin(K, typed_float, true, nprog, prog, &cubin, &why);  // both staging variants
   if (!ok && why.empty()) why = g_api.why;
   if (log && loglen > 0) {
     std::string msg = ok ? ("ok cubin bytes=" + std::to_string(cubin.size())) : why;

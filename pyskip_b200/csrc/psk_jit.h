@@ -26,7 +26,7 @@ struct JitKernel {
 
 // Returns nullptr when JIT is unavailable/disabled or compilation failed (the reason is
 // appended to *why when given).
-const JitKernel* jit_get_merge_eval(int K, bool typed_float, int nprog, const psk_node* prog, const char** why);
+const JitKernel* jit_get_merge_eval(int K, bool typed_float, bool views, int nprog, const psk_node* prog, const char** why);
 
 // cuLaunchKernel on `stream`; returns 0 on success.
 int jit_launch(const JitKernel* k, unsigned grid, unsigned block, size_t smem, void* stream, void* plan_ptr);

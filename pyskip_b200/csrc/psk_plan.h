@@ -77,17 +77,25 @@ PSK_HD uint32_t map_gather(const DView& v, uint32_t E) {
   if (E >= v.n) return v.m;
   uint32_t out = 0, rem = E;
   for (int d = v.ndim - 1; d >= 0; --d) {
-    uint32_t x = rem / v.scale[d];
-    rem -= x * v.scale[d];
-    uint32_t below;
-    if (x <= v.c0[d]) {
-      below = 0;
+    const uint32_t sc = v.scale[d], c0 = v.c0[d], cs = v.cs[d];
+    uint32_t x = rem;
+    if (sc != 1) {  // dim 0 has unit stride: no division
+      x = rem / sc;
+      rem -= x * sc;
+    }
+    uint32_t below = 0;
+    bool sel;
+    if (cs == 1) {  // contiguous selection (plain boxes, convolution taps): no division
+      if (x > c0) below = x - c0 < v.cnt[d] ? x - c0 : v.cnt[d];
+      sel = x >= c0 && x < v.c1[d];
     } else {
-      below = (x - v.c0[d] + v.cs[d] - 1) / v.cs[d];
-      if (below > v.cnt[d]) below = v.cnt[d];
+      if (x > c0) {
+        below = (x - c0 + cs - 1) / cs;
+        if (below > v.cnt[d]) below = v.cnt[d];
+      }
+      sel = x >= c0 && x < v.c1[d] && ((x - c0) % cs) == 0;
     }
     out += below * v.inner[d];
-    bool sel = x >= v.c0[d] && x < v.c1[d] && ((x - v.c0[d]) % v.cs[d]) == 0;
     if (!sel) break;
   }
   return out;

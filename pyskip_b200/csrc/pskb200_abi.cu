@@ -888,7 +888,7 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
   cudaError_t e = cudaMemsetAsync(scratch, 0, o_merged, g.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_plan, &hp, plan_bytes, cudaMemcpyHostToDevice, g.stream);
   if (e == cudaSuccess) {
-    if (any_views) LAUNCH(k_prepare, 1, 32, 0, d_plan);
+    if (any_views) LAUNCH(k_prepare, 1, 32 * k, 0, d_plan);
     LAUNCH(k_sample_keys, (unsigned)((max_samples + 255) / 256), 256, 0, d_plan);
     LAUNCH(k_sample_rank, (unsigned)((max_samples + 255) / 256), 256, 0, d_plan);
     LAUNCH(k_tile_bounds, (unsigned)(((max_tiles + 1) * k + 255) / 256), 256, 0, d_plan);
@@ -901,7 +901,7 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
     if (total_runs >= g.jit_min_runs) {
       // the same kernel template with the program compiled in (psk_jit.h)
       // K = k exactly: no padding sources in the specialised kernel
-      if (const JitKernel* jk = jit_get_merge_eval(k, hp.eq != 0, nprog, prog, nullptr)) {
+      if (const JitKernel* jk = jit_get_merge_eval(k, hp.eq != 0, any_views, nprog, prog, nullptr)) {
         if (jit_launch(jk, (unsigned)grid, kTileThreads, kMergeEvalSmemBytes, g.stream, d_plan) == 0) {
           launched = true;
           g.launches.fetch_add(1, std::memory_order_relaxed);
