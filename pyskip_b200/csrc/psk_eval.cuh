@@ -714,46 +714,27 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
 
     PSK_PHASE(2);  // per-thread binary searches
     // ---- sequential k-way merge over (c0, c1] -------------------------------------------
-    // One run is consumed per iteration (one 64-bit shared load per lane); sources that
-    // share an end are drained by further iterations that see e == last_e and emit nothing.
+    // One distinct end is consumed per iteration: every source whose head run ends there
+    // moves on to its next run (one predicated 64-bit shared load per source).
     int32_t n = 0;
     bool have = false;
-    int32_t pe = 0, last_e = c0;
+    int32_t pe = 0;
     uint32_t pv = 0;
     for (;;) {
       int32_t e = head[0];
 #pragma unroll
       for (int i = 1; i < K; ++i) e = imin(e, head[i]);
       if (e > c1) break;
-      if (e != last_e) {
-        const uint32_t v = ev(val);  // value of the span that ends at e
-        if (have && !payload_equal(pv, v, typed_float)) {
-          sm.st(IN_N + base + n, pe, (int32_t)pv);
-          ++n;
-        }
-        pe = e;
-        pv = v;
-        have = true;
-        last_e = e;
+      const uint32_t v = ev(val);  // value of the span that ends at e
+      if (have && !payload_equal(pv, v, typed_float)) {
+        sm.st(IN_N + base + n, pe, (int32_t)pv);
+        ++n;
       }
-      int32_t idx = 0;
-      int j = K;
+      pe = e;
+      pv = v;
+      have = true;
 #pragma unroll
-      for (int i = K - 1; i >= 0; --i) {
-        if (head[i] == e) {
-          j = i;
-          idx = cur[i];
-        }
-      }
-      const int2 nx = sm.ld(idx + 1);
-#pragma unroll
-      for (int i = 0; i < K; ++i) {
-        if (i == j) {
-          cur[i] = idx + 1;
-          head[i] = nx.x;
-          val[i] = (uint32_t)nx.y;
-        }
-      }
+      for (int i = 0; i < K; ++i) sm.advance_if(e, cur[i], head[i], val[i]);
     }
     if (have) {
       // the thread's last span: kept iff it is the last span of the array or the NEXT

@@ -73,9 +73,25 @@ struct SmemPairs {
   PSK_D void st(int i, int x, int y) const {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base + (uint32_t)i * 8u), "r"(x), "r"(y) : "memory");
   }
+  // merge step of one source: if its head run ends at e, move on to its next run
+  // (predicated load: no branch, no select chain)
+  PSK_D void advance_if(int e, int& cur, int& head, uint32_t& val) const {
+    asm volatile(
+        "{\n .reg .pred q;\n setp.eq.s32 q, %0, %3;\n @q add.s32 %2, %2, 1;\n"
+        " @q ld.shared.v2.b32 {%0, %1}, [%4+8];\n}"
+        : "+r"(head), "+r"(val), "+r"(cur)
+        : "r"(e), "r"(base + (uint32_t)cur * 8u));
+  }
 #else
   int2* ptr;
   explicit SmemPairs(void* p) : ptr(reinterpret_cast<int2*>(p)) {}
+  void advance_if(int e, int& cur, int& head, uint32_t& val) const {
+    if (head == e) {
+      ++cur;
+      head = ptr[cur].x;
+      val = (uint32_t)ptr[cur].y;
+    }
+  }
   int2 ld(int i) const { return ptr[i]; }
   int ldx(int i) const { return ptr[i].x; }
   void st(int i, int x, int y) const { ptr[i] = make_int2(x, y); }

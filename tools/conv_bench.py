@@ -58,6 +58,17 @@ for _ in range(reps):
     E.synchronize()
     times.append(time.perf_counter() - t0)
 print("per-conv ms:", [round(x * 1e3, 2) for x in times])
+if os.environ.get("PSK_CONV_CPROFILE") == "1":
+    import cProfile, pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(5):
+        out = ps.functional.conv_3d(t, k, padding=1)
+        E.synchronize()
+    pr.disable()
+    pstats.Stats(pr).sort_stats("tottime").print_stats(14)
+    tm = lib.c.psk_timer_start
+    sys.exit(0)
 dt = float(np.median(times))
 ms, nev, ri, ro = lib.profile_read()
 print(f"conv_3d {n}^3: runs in {r_in} ({r_in / vol.size * 100:.2f} %), runs out {r_out}; "
