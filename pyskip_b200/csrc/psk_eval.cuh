@@ -699,6 +699,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
         }
       }
     }
+    uint32_t cur_at[K];  // cursors (shared-window addresses) of the k head runs
 #pragma unroll
     for (int i = 0; i < K; ++i) {
       if (i < k && !fail) {
@@ -710,13 +711,15 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
         head[i] = kSentinel;
         val[i] = 0;
       }
+      cur_at[i] = sm.at(cur[i]);
     }
+    const uint32_t out_begin = sm.at(IN_N + base);
+    uint32_t out_at = out_begin;  // where this thread's next kept span goes
 
     PSK_PHASE(2);  // per-thread binary searches
     // ---- sequential k-way merge over (c0, c1] -------------------------------------------
     // One distinct end is consumed per iteration: every source whose head run ends there
     // moves on to its next run (one predicated 64-bit shared load per source).
-    int32_t n = 0;
     bool have = false;
     int32_t pe = 0;
     uint32_t pv = 0;
@@ -727,14 +730,14 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
       if (e > c1) break;
       const uint32_t v = ev(val);  // value of the span that ends at e
       if (have && !payload_equal(pv, v, typed_float)) {
-        sm.st(IN_N + base + n, pe, (int32_t)pv);
-        ++n;
+        sm.st_at(out_at, pe, (int32_t)pv);
+        out_at += sm.step();
       }
       pe = e;
       pv = v;
       have = true;
 #pragma unroll
-      for (int i = 0; i < K; ++i) sm.advance_if(e, cur[i], head[i], val[i]);
+      for (int i = 0; i < K; ++i) sm.advance_if(e, cur_at[i], head[i], val[i]);
     }
     if (have) {
       // the thread's last span: kept iff it is the last span of the array or the NEXT
@@ -742,10 +745,11 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
       bool keep = (pe == span);
       if (!keep) keep = !payload_equal(pv, ev(val), typed_float);
       if (keep) {
-        sm.st(IN_N + base + n, pe, (int32_t)pv);
-        ++n;
+        sm.st_at(out_at, pe, (int32_t)pv);
+        out_at += sm.step();
       }
     }
+    const int32_t n = (int32_t)((out_at - out_begin) / sm.step());  // spans this thread keeps
 
     PSK_PHASE(3);  // thread 0's own merge loop
     // ---- compaction: block scan; the cross-tile look-back and the global write of a tile

@@ -73,23 +73,33 @@ struct SmemPairs {
   PSK_D void st(int i, int x, int y) const {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base + (uint32_t)i * 8u), "r"(x), "r"(y) : "memory");
   }
+  // A cursor is the shared-window byte address of a pair: loops that walk the buffer keep
+  // cursors in registers and never recompute base + 8 * index.
+  PSK_D uint32_t at(int i) const { return base + (uint32_t)i * 8u; }
+  static PSK_D uint32_t step() { return 8u; }
+  PSK_D void st_at(uint32_t c, int x, int y) const {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(c), "r"(x), "r"(y) : "memory");
+  }
   // merge step of one source: if its head run ends at e, move on to its next run
   // (predicated load: no branch, no select chain)
-  PSK_D void advance_if(int e, int& cur, int& head, uint32_t& val) const {
+  PSK_D void advance_if(int e, uint32_t& c, int& head, uint32_t& val) const {
     asm volatile(
-        "{\n .reg .pred q;\n setp.eq.s32 q, %0, %3;\n @q add.s32 %2, %2, 1;\n"
-        " @q ld.shared.v2.b32 {%0, %1}, [%4+8];\n}"
-        : "+r"(head), "+r"(val), "+r"(cur)
-        : "r"(e), "r"(base + (uint32_t)cur * 8u));
+        "{\n .reg .pred q;\n setp.eq.s32 q, %0, %3;\n @q add.u32 %2, %2, 8;\n"
+        " @q ld.shared.v2.b32 {%0, %1}, [%2];\n}"
+        : "+r"(head), "+r"(val), "+r"(c)
+        : "r"(e));
   }
 #else
   int2* ptr;
   explicit SmemPairs(void* p) : ptr(reinterpret_cast<int2*>(p)) {}
-  void advance_if(int e, int& cur, int& head, uint32_t& val) const {
+  uint32_t at(int i) const { return (uint32_t)i; }
+  static uint32_t step() { return 1u; }
+  void st_at(uint32_t c, int x, int y) const { ptr[c] = make_int2(x, y); }
+  void advance_if(int e, uint32_t& c, int& head, uint32_t& val) const {
     if (head == e) {
-      ++cur;
-      head = ptr[cur].x;
-      val = (uint32_t)ptr[cur].y;
+      ++c;
+      head = ptr[c].x;
+      val = (uint32_t)ptr[c].y;
     }
   }
   int2 ld(int i) const { return ptr[i]; }
