@@ -39,6 +39,9 @@ namespace psk {
 #endif
 constexpr int kTileThreads = PSK_TILE_THREADS;
 constexpr int kTileCap = PSK_TILE_CAP;  // runs of all sources staged per tile (excl. look-ahead)
+#ifndef PSK_COARSE_SEARCH
+#define PSK_COARSE_SEARCH 1
+#endif
 constexpr int kSentinel = 0x7fffffff;
 
 // dynamic shared memory of k_merge_eval: in[CAP + 32] | out[CAP] | pending[CAP] (8-byte pairs)
@@ -306,7 +309,8 @@ PSK_D void publish_aggregate(unsigned long long* state, int32_t tile, int32_t co
 // every predecessor is resident or finished and the spin cannot deadlock.
 template <int T>
 PSK_D int32_t lookback_exclusive_cta(unsigned long long* state, int32_t tile, int32_t count,
-                                     int32_t* s_sum /*[T/32]*/, int32_t* s_has /*[T/32]*/) {
+                                     unsigned long long early, int32_t* s_sum /*[T/32]*/,
+                                     int32_t* s_has /*[T/32]*/) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tile == 0) return 0;
   int32_t excl = 0;
@@ -314,9 +318,10 @@ PSK_D int32_t lookback_exclusive_cta(unsigned long long* state, int32_t tile, in
     const int32_t idx = j - tid;
     unsigned long long w = (unsigned long long)ST_PREFIX << 32;  // virtual prefix 0 before tile 0
     if (idx >= 0) {
-      do {
-        w = ld_volatile_u64(&state[idx]);
-      } while ((w >> 32) == ST_INVALID);
+      // first round: the word this thread loaded before the merge (lookback_peek), if it was
+      // already published then
+      w = (j == tile - 1) ? early : 0ull;
+      while ((w >> 32) == ST_INVALID) w = ld_volatile_u64(&state[idx]);
     }
     const unsigned pmask = __ballot_sync(0xffffffffu, (w >> 32) == ST_PREFIX);
     const int first = pmask ? (__ffs((int)pmask) - 1) : 32;
@@ -329,15 +334,15 @@ PSK_D int32_t lookback_exclusive_cta(unsigned long long* state, int32_t tile, in
       s_has[warp] = pmask != 0;
     }
     __syncthreads();
-    bool done = false;
-    for (int q = 0; q < T / 32; ++q) {  // every thread folds the warp results in tile order
-      excl += s_sum[q];
-      if (s_has[q]) {
-        done = true;
-        break;
-      }
-    }
-    if (done) break;
+    // every warp folds the warp results in tile order: lane q holds warp q's
+    const int32_t ws = (lane < T / 32) ? s_sum[lane] : 0;
+    const unsigned hmask = __ballot_sync(0xffffffffu, lane < T / 32 && s_has[lane] != 0);
+    const int fw = hmask ? (__ffs((int)hmask) - 1) : 32;
+    int32_t part = (lane <= fw) ? ws : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    excl += part;
+    if (hmask) break;
   }
   __syncthreads();
   if (tid == 0)
@@ -345,13 +350,21 @@ PSK_D int32_t lookback_exclusive_cta(unsigned long long* state, int32_t tile, in
   return excl;
 }
 
+// The look-back word a thread will need for `tile`, loaded early (before the merge of the
+// next tile) so that its latency is off the critical path; 0 (INVALID) if there is none.
+template <int T>
+PSK_D unsigned long long lookback_peek(const unsigned long long* state, int32_t tile) {
+  const int32_t idx = tile - 1 - (int32_t)threadIdx.x;
+  return (tile > 0 && idx >= 0) ? ld_volatile_u64(&state[idx]) : 0ull;
+}
+
 // Resolve the global offset of a finished tile whose compacted spans wait at sm[region..] and
 // write them out (coalesced).  Called by the whole CTA.
 template <int T>
 PSK_D void flush_pending(DPlan* p, const SmemPairs& sm, int region, int32_t tile, int32_t total,
-                         int32_t n_tiles, int32_t* s_sum, int32_t* s_has) {
+                         unsigned long long early, int32_t n_tiles, int32_t* s_sum, int32_t* s_has) {
   const int tid = threadIdx.x;
-  const int32_t gofs = lookback_exclusive_cta<T>(p->tile_state, tile, total, s_sum, s_has);
+  const int32_t gofs = lookback_exclusive_cta<T>(p->tile_state, tile, total, early, s_sum, s_has);
   if (tid == 0 && tile == n_tiles - 1) p->ctrl[CTRL_COUNT] = gofs + total;
   if (gofs + total <= p->out_capacity) {
     for (int32_t j = tid; j < total; j += T) {
@@ -441,10 +454,16 @@ PSK_D void store_tile_desc(const DescRegs& r, TileDesc* d, int k) {
 // Where the RAW runs of a tile go in the shared tile buffer: the sources occupy the flat
 // slots [0, flat_total) back to back (slice + one look-ahead run each).  With views the
 // staging pass then maps the ends and squeezes out zero-length mapped runs in place.
+struct SlotSource {  // ebase[j] / vbase[j] = the run that belongs in flat slot j
+  const int32_t* ebase;
+  const uint32_t* vbase;
+};
 struct TileLayout {
   int32_t off[PSK_MAX_SOURCES + 1];
   int32_t len[PSK_MAX_SOURCES];  // staged runs (excl. look-ahead)
+  int32_t lim[PSK_MAX_SOURCES];  // slots of the source below lim hold a run, the rest a sentinel
   int32_t flat_total;
+  alignas(16) SlotSource ss[PSK_MAX_SOURCES];
 };
 
 // one warp: layout of tile d
@@ -459,8 +478,13 @@ PSK_D void compute_layout(const TileDesc& d, const SrcDesc* src, int k, TileLayo
     if (lane >= dd) inc += o;
   }
   if (lane < k) {
-    L->off[lane] = inc - len;
+    const int32_t off = inc - len;
+    L->off[lane] = off;
     L->len[lane] = len ? len - 1 : 0;
+    // the look-ahead slot holds a run only if the source has one beyond the tile
+    L->lim[lane] = off + imin(len, src[lane].e - d.b0[lane]);
+    L->ss[lane].ebase = src[lane].ends + (d.b0[lane] - off);
+    L->ss[lane].vbase = src[lane].vals + (d.b0[lane] - off);
   }
   if (lane == 31) L->flat_total = inc;
 }
@@ -486,21 +510,48 @@ PSK_D int slot_owner(const int32_t* off, int k, int32_t j) {
 // all threads: issue the global loads of the tile's raw runs into registers (flat
 // slot j = tid + u*T).  Nothing waits on them here; they are stored to shared memory one
 // tile later, so the HBM latency overlaps the merge of the tile in front.
-template <int K, int T, int NB>
+template <int K, int T, int NB, int U0 = 0, int U1 = NB>
 PSK_D void issue_tile_loads(const TileDesc& d, const TileLayout& L, const SrcDesc* src, int k, int32_t limit,
                             int2 (&pr)[NB]) {
-  const int32_t used = L.flat_total;
+  const int32_t used = L.flat_total <= limit ? L.flat_total : 0;
+  // branch-free, four slots at a time: owner -> (limit, bases) from shared memory -> two
+  // predicated global loads; nothing in here waits for a global load
+  int32_t off_[K <= 8 ? K : 1];
+  if (K <= 8) {
 #pragma unroll
-  for (int u = 0; u < NB; ++u) {
-    const int32_t j = (int32_t)threadIdx.x + u * T;
-    pr[u] = make_int2(kSentinel, 0);  // no run beyond the tile: sentinel look-ahead
-    if (j < used && used <= limit) {
-      const int i = slot_owner<K>(L.off, k, j);
-      const int32_t r = j - L.off[i];
-      const int32_t idx = d.b0[i] + r;
-      if (r < L.len[i] || idx < src[i].e) {
-        pr[u].x = ld_nc(src[i].ends + idx);
-        pr[u].y = (int32_t)ld_nc(src[i].vals + idx);
+    for (int q = 1; q < K; ++q) off_[q] = (q < k) ? L.off[q] : kSentinel;
+  }
+  constexpr int G = 4;
+#pragma unroll
+  for (int u0 = U0; u0 < U1; u0 += G) {
+    int i_[G];
+    int32_t lim_[G];
+    SlotSource ss_[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int32_t j = (int32_t)threadIdx.x + (u0 + g) * T;
+      int i = 0;
+      if (K <= 8) {
+#pragma unroll
+        for (int q = 1; q < K; ++q) i += (off_[q] <= j) ? 1 : 0;
+      } else {
+        i = slot_owner<K>(L.off, k, j);
+      }
+      i_[g] = i;
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      lim_[g] = L.lim[i_[g]];
+      ss_[g] = L.ss[i_[g]];
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      if (u0 + g < U1) {
+        const int32_t j = (int32_t)threadIdx.x + (u0 + g) * T;
+        // no run in the slot (beyond the tile / the source): sentinel look-ahead
+        const bool take = j < used && j < lim_[g];
+        pr[u0 + g].x = ld_nc_if(ss_[g].ebase + j, take, kSentinel);
+        pr[u0 + g].y = ld_nc_if(reinterpret_cast<const int32_t*>(ss_[g].vbase) + j, take, 0);
       }
     }
   }
@@ -526,6 +577,9 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
   __shared__ SrcDesc s_src[PSK_MAX_SOURCES];
   __shared__ int32_t s_warp[T / 32 + 2];
   __shared__ int32_t s_lbhas[T / 32];
+#if PSK_COARSE_SEARCH
+  __shared__ unsigned short s_coarse[PSK_MAX_SOURCES * (T / 8 + 1)];  // cursors of every 8th thread
+#endif
   __shared__ int32_t s_newoff[PSK_MAX_SOURCES];  // with views: slot layout after the squeeze
   __shared__ int32_t s_newend[PSK_MAX_SOURCES];
 
@@ -666,7 +720,12 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     PSK_PHASE(1);  // staging
     if (fail && tid == 0) p->ctrl[CTRL_ERROR] = 1;
     // the next tile's loads go out now and land while this tile is merged
-    if (next_valid) issue_tile_loads<K, T, NB>(dn, s_layout[(it + 1) & 1], s_src, k, IN_N, pr);
+    // (in four bursts spread over the tile's phases: one burst of the whole tile overruns
+    //  what the SM keeps in flight towards HBM and stalls the issuing warps)
+    constexpr int NQ = (NB + 3) / 4;  // slots per burst
+    const TileLayout& lay_next = s_layout[(it + 1) & 1];
+    if (next_valid) issue_tile_loads<K, T, NB, 0, (NQ < NB ? NQ : NB)>(dn, lay_next, s_src, k, IN_N, pr);
+    PSK_PHASE(7);  // issuing the next tile's loads
 
     // ---- split the tile's coordinate range (lo, hi] over the threads --------------------
     const long long width = (long long)hi - lo;
@@ -674,15 +733,50 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     const int32_t c1 = lo + (int32_t)((width * (tid + 1)) / T);
 
     // first staged run of every source whose end is > c0: branch-free binary searches that
-    // advance in lock step over the sources (the look-ahead run bounds each of them)
+    // advance in lock step over the sources (the look-ahead run bounds each of them).
+    // Coarse to fine: the cursors of every CG-th thread are found first (one search per
+    // thread, over the whole slice) and bracket the searches of the threads in between --
+    // roughly half the shared-memory probes of T * k full searches.
     int32_t cur[K], head[K], rem[K];
     uint32_t val[K];
     int32_t base = 0;
+#if PSK_COARSE_SEARCH
+    constexpr int CG = 8, NC = T / CG;
+    if (!fail) {
+      for (int32_t q = tid; q < NC * k; q += T) {
+        const int i = q / NC, g = q - i * NC;
+        const int32_t cg = lo + (int32_t)((width * (g * CG)) / T);
+        int32_t c = s_off[i], r = s_len[i] + 1;
+        while (r > 1) {
+          const int32_t half = r >> 1;
+          c += (sm.ldx(c + half - 1) <= cg) ? half : 0;
+          r -= half;
+        }
+        s_coarse[i * (NC + 1) + g] = (unsigned short)c;
+        if (g == 0) s_coarse[i * (NC + 1) + NC] = (unsigned short)(s_off[i] + s_len[i]);
+      }
+    }
+    if (next_valid) issue_tile_loads<K, T, NB, (NQ < NB ? NQ : NB), (2 * NQ < NB ? 2 * NQ : NB)>(dn, lay_next, s_src, k, IN_N, pr);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      if (i < k && !fail) {
+        const int32_t a0 = s_coarse[i * (NC + 1) + tid / CG], a1 = s_coarse[i * (NC + 1) + tid / CG + 1];
+        cur[i] = a0;
+        rem[i] = a1 - a0 + 1;
+      } else {
+        cur[i] = 0;
+        rem[i] = 1;
+      }
+    }
+#else
+    if (next_valid) issue_tile_loads<K, T, NB, (NQ < NB ? NQ : NB), (2 * NQ < NB ? 2 * NQ : NB)>(dn, lay_next, s_src, k, IN_N, pr);
 #pragma unroll
     for (int i = 0; i < K; ++i) {
       cur[i] = (i < k) ? s_off[i] : 0;
       rem[i] = (i < k && !fail) ? s_len[i] + 1 : 1;
     }
+#endif
     {
       int32_t longest = 1;
 #pragma unroll
@@ -716,6 +810,9 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     const uint32_t out_begin = sm.at(IN_N + base);
     uint32_t out_at = out_begin;  // where this thread's next kept span goes
 
+    if (next_valid) issue_tile_loads<K, T, NB, (2 * NQ < NB ? 2 * NQ : NB), (3 * NQ < NB ? 3 * NQ : NB)>(dn, lay_next, s_src, k, IN_N, pr);
+    // the look-back word of the tile that is flushed after this merge: in flight meanwhile
+    const unsigned long long lb_early = pend_tile >= 0 ? lookback_peek<T>(p->tile_state, pend_tile) : 0ull;
     PSK_PHASE(2);  // per-thread binary searches
     // ---- sequential k-way merge over (c0, c1] -------------------------------------------
     // One distinct end is consumed per iteration: every source whose head run ends there
@@ -751,6 +848,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     }
     const int32_t n = (int32_t)((out_at - out_begin) / sm.step());  // spans this thread keeps
 
+    if (next_valid) issue_tile_loads<K, T, NB, (3 * NQ < NB ? 3 * NQ : NB), NB>(dn, lay_next, s_src, k, IN_N, pr);
     PSK_PHASE(3);  // thread 0's own merge loop
     // ---- compaction: block scan; the cross-tile look-back and the global write of a tile
     //      are DEFERRED by one tile: its run count is published right after the scan, its
@@ -761,7 +859,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     const int32_t my_ofs = block_exclusive_scan<T>(n, s_warp, &tile_total);
     PSK_PHASE(4);  // waiting for the slowest thread + scan
     if (tid == 0) publish_aggregate(p->tile_state, tile, tile_total);
-    if (pend_tile >= 0) flush_pending<T>(p, sm, PEND, pend_tile, pend_total, n_tiles, s_warp, s_lbhas);
+    if (pend_tile >= 0) flush_pending<T>(p, sm, PEND, pend_tile, pend_total, lb_early, n_tiles, s_warp, s_lbhas);
     PSK_PHASE(5);  // look-back + global write of the previous tile
     for (int32_t j = 0; j < n; ++j) {
       const int2 r = sm.ld(IN_N + base + j);
@@ -773,7 +871,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     __syncthreads();
     PSK_PHASE(6);  // smem compaction
   }
-  if (pend_tile >= 0) flush_pending<T>(p, sm, PEND, pend_tile, pend_total, n_tiles, s_warp, s_lbhas);
+  if (pend_tile >= 0) flush_pending<T>(p, sm, PEND, pend_tile, pend_total, 0ull, n_tiles, s_warp, s_lbhas);
   PSK_PHASE_FLUSH;
 }
 

@@ -222,6 +222,9 @@ bool compile_cubin(int K, bool typed_float, bool views, int nprog, const psk_nod
 #ifdef PSK_TILE_CAP
                         "-DPSK_TILE_CAP=" PSK_STR(PSK_TILE_CAP),
 #endif
+#ifdef PSK_COARSE_SEARCH
+                        "-DPSK_COARSE_SEARCH=" PSK_STR(PSK_COARSE_SEARCH),
+#endif
 #ifdef PSK_LOOKBACK_WARP
                         "-DPSK_LOOKBACK_WARP",
 #endif

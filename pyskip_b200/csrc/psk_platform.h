@@ -50,6 +50,19 @@ PSK_D uint32_t ld_nc(const uint32_t* p) {
 #endif
 }
 
+// predicated read-only load: *p if take, else dflt -- one @p LDG, never a branch
+PSK_D int32_t ld_nc_if(const int32_t* p, bool take, int32_t dflt) {
+#if defined(__CUDA_ARCH__)
+  int32_t r;
+  asm volatile("{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n mov.b32 %0, %3;\n @q ld.global.nc.b32 %0, [%1];\n}"
+               : "=&r"(r)
+               : "l"(p), "r"((int)take), "r"(dflt));
+  return r;
+#else
+  return take ? *p : dflt;
+#endif
+}
+
 // The tile buffer in dynamic shared memory, addressed by 32-bit shared-window offsets with
 // explicit ld.shared / st.shared: nvcc otherwise re-derives the generic address of dynamic
 // shared memory (S2R SR_CgaCtaId + LEA) inside the merge loop.
