@@ -280,12 +280,32 @@ def main():
     srcs = [(s, []) for s in resident]
 
     step_no = [0]
+    # The resident step goes through psk_eval_async: the kernels are queued and the call
+    # returns; a result's run count is read two steps later, so the host work of step i+1
+    # (plan, launches) overlaps the kernels of step i.  Every result is completed and checked
+    # before the timed region ends.
+    eval_resident = lib.prepare_eval(srcs, prog, A.F32, A.EQ_BITWISE, deferred=True)
+    inflight = []
+    expect_runs = [None]
+
+    def complete(res):
+        n = res.nruns                      # waits for that step's kernels
+        if expect_runs[0] is None:
+            expect_runs[0] = n
+        assert n == expect_runs[0] and n > 0, f"step produced {n} runs, expected {expect_runs[0]}"
 
     def step_resident():
-        res = lib.eval(srcs, prog, A.F32, A.EQ_BITWISE)
+        res = eval_resident()
         stitch(res, step_no[0])
         step_no[0] += 1
+        inflight.append(res)
+        while len(inflight) > 2:
+            complete(inflight.pop(0))
         return res
+
+    def drain_resident():
+        while inflight:
+            complete(inflight.pop(0))
 
     def barrier():
         if dist is not None:
@@ -295,6 +315,7 @@ def main():
 
     for _ in range(args.warmup):
         res = step_resident()
+    drain_resident()
     runs_out = res.nruns
     del res
     stitch_drain()
@@ -309,9 +330,9 @@ def main():
     t0 = time.time()
     lib.timer_start()
     for _ in range(args.steps):
-        res = step_resident()
-        del res
-    total_out = stitch_drain()            # every step's exchange has completed inside the region
+        step_resident()
+    drain_resident()                      # every step's result is complete and checked ...
+    total_out = stitch_drain()            # ... and every step's exchange has completed inside the region
     ms_total = lib.timer_stop()
     barrier()
     t1 = time.time()
@@ -343,7 +364,10 @@ def main():
         pending = upload_async()
         prev = None
         n_out = 0
+        verbose = os.environ.get("BENCH_E2E_VERBOSE") == "1"
         for i in range(n):
+            if verbose:
+                print(f"e2e step {i} starts at {time.perf_counter() * 1e3:.2f} ms", file=sys.stderr)
             nxt = upload_async() if i + 1 < n else None
             r = lib.eval([(s, []) for s in pending], prog, A.F32, A.EQ_BITWISE)
             n_out = r.nruns

@@ -232,6 +232,17 @@ PSK_API void psk_store_release(psk_store_t s);
 PSK_API psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog,
                             const psk_node* prog, psk_dtype out_dtype, psk_eq eq,
                             psk_store_t* out);
+
+/* psk_eval without the final wait: the kernels are queued on the library stream and the call
+ * returns at once.  The result's run count (and any error of the evaluation) is fetched when
+ * the store is first USED -- psk_store_nruns (returns -1 on error), psk_store_runs, a later
+ * psk_eval that takes it as a source, ... -- so back-to-back evaluations overlap their host
+ * work with the previous one's kernels.  Up to 32 results may be outstanding; more complete
+ * the oldest first.  Same arguments and results as psk_eval; the reference has no
+ * counterpart (its eval_simple, detail/eval.hpp:632-659, is synchronous). */
+PSK_API psk_status psk_eval_async(int32_t k, const psk_source* sources, int32_t nprog,
+                                  const psk_node* prog, psk_dtype out_dtype, psk_eq eq,
+                                  psk_store_t* out);
 /* Output span of a source view chain applied to a store span (lang::slice, lang.hpp:162). */
 PSK_API psk_status psk_view_span(int32_t span_in, int32_t nviews, const psk_view* views,
                                  int32_t* span_out);

@@ -107,7 +107,7 @@ _SYMBOLS = [
     "psk_live_bytes", "psk_profile", "psk_profile_read", "psk_set_jit_threshold", "psk_jit_launch_count", "psk_jit_compile_check", "psk_store_from_runs", "psk_store_from_runs_async", "psk_store_runs_async", "psk_copy_synchronize", "psk_store_from_device_runs", "psk_store_fill",
     "psk_store_from_dense", "psk_store_from_dense_device", "psk_store_to_dense",
     "psk_store_to_dense_device", "psk_store_runs", "psk_store_nruns", "psk_store_span",
-    "psk_store_dtype", "psk_store_device_ptrs", "psk_store_first_value", "psk_store_retain",
+    "psk_store_dtype", "psk_store_device_ptrs", "psk_store_first_value", "psk_eval_async", "psk_store_retain",
     "psk_store_release", "psk_eval", "psk_view_span", "psk_mask_nd", "psk_reduce",
     "psk_store_boundary", "psk_store_boundary_device", "psk_store_slice",
 ]
@@ -132,7 +132,10 @@ class Store:
 
     @property
     def nruns(self) -> int:
-        return self.lib.c.psk_store_nruns(C.c_void_p(self.h))
+        n = self.lib.c.psk_store_nruns(C.c_void_p(self.h))
+        if n < 0:  # a deferred evaluation (psk_eval_async) that failed
+            raise PskError(self.lib.c.psk_last_error().decode())
+        return n
 
     @property
     def span(self) -> int:
@@ -203,6 +206,7 @@ class Lib:
         c.psk_store_boundary.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         c.psk_store_slice.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         c.psk_eval.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        c.psk_eval_async.argtypes = c.psk_eval.argtypes
         c.psk_view_span.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         c.psk_mask_nd.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         c.psk_reduce.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -352,6 +356,30 @@ class Lib:
         h = C.c_void_p()
         self._chk(self.c.psk_eval(k, arr, len(prog), nodes, out_dtype, eq, C.byref(h)))
         return Store(self, h.value)
+
+    def prepare_eval(self, sources, prog, out_dtype: int, eq: int = EQ_BITWISE, deferred: bool = False):
+        """Marshal (sources, prog) once; the returned callable runs the evaluation (psk_eval, or
+        psk_eval_async when `deferred`: the result's run count is fetched on first use)."""
+        k = len(sources)
+        arr = (Source * max(k, 1))()
+        for i, (st, views) in enumerate(sources):
+            arr[i].store = st.h
+            arr[i].nviews = len(views)
+            for j, v in enumerate(views):
+                arr[i].views[j] = v
+        nodes = (Node * max(len(prog), 1))()
+        for i, (op, arg) in enumerate(prog):
+            nodes[i].op = int(op)
+            nodes[i].arg = int(arg) & 0xFFFFFFFF
+        fn = self.c.psk_eval_async if deferred else self.c.psk_eval
+        keep = list(sources)  # the source stores must outlive the callable
+
+        def run():
+            h = C.c_void_p()
+            self._chk(fn(k, arr, len(prog), nodes, out_dtype, eq, C.byref(h)))
+            return Store(self, h.value)
+        run._keep = keep
+        return run
 
     def view_span(self, span_in: int, views) -> int:
         arr = (View * max(len(views), 1))(*views)

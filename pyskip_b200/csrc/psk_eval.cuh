@@ -210,17 +210,34 @@ __global__ void k_sample_rank(DPlan* p) {
   const int i = sample_owner(s_off, k, sid);
   const int32_t key = keys[sid];
   int32_t rank = sid - s_off[i];
-  for (int q = 0; q < k; ++q) {
-    if (q == i) continue;
-    const int32_t* const kq = keys + s_off[q];
-    int32_t lo = 0, hi = s_ns[q];
-    while (lo < hi) {
-      const int32_t mid = lo + ((hi - lo) >> 1);
-      const int32_t v = kq[mid];
-      const bool before = (q < i) ? (v <= key) : (v < key);
-      if (before) lo = mid + 1; else hi = mid;
+  // the searches over the other sources advance in lock step, eight at a time: their loads
+  // are independent, so the (L2) latencies overlap instead of adding up
+  constexpr int W = 8;
+  for (int q0 = 0; q0 < k; q0 += W) {
+    int32_t pos[W], len[W];
+    int32_t longest = 0;
+#pragma unroll
+    for (int u = 0; u < W; ++u) {
+      const int q = q0 + u;
+      pos[u] = 0;
+      len[u] = (q < k && q != i) ? s_ns[q] : 0;
+      longest = imax(longest, len[u]);
     }
-    rank += lo;
+    for (; longest > 0; longest >>= 1) {
+#pragma unroll
+      for (int u = 0; u < W; ++u) {
+        const int q = q0 + u;
+        if (len[u] > 0) {
+          const int32_t half = len[u] >> 1;
+          const int32_t v = keys[s_off[q < k ? q : 0] + pos[u] + half];
+          const bool before = (q < i) ? (v <= key) : (v < key);
+          pos[u] += before ? half + 1 : 0;
+          len[u] = before ? len[u] - half - 1 : half;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < W; ++u) rank += pos[u];
   }
   p->merged[rank] = key;
 }
@@ -365,7 +382,10 @@ PSK_D void flush_pending(DPlan* p, const SmemPairs& sm, int region, int32_t tile
                          unsigned long long early, int32_t n_tiles, int32_t* s_sum, int32_t* s_has) {
   const int tid = threadIdx.x;
   const int32_t gofs = lookback_exclusive_cta<T>(p->tile_state, tile, total, early, s_sum, s_has);
-  if (tid == 0 && tile == n_tiles - 1) p->ctrl[CTRL_COUNT] = gofs + total;
+  if (tid == 0 && tile == n_tiles - 1) {
+    p->ctrl[CTRL_COUNT] = gofs + total;
+    p->out_ends[p->out_capacity] = gofs + total;  // spare word: the count stays on the device too
+  }
   if (gofs + total <= p->out_capacity) {
     for (int32_t j = tid; j < total; j += T) {
       const int2 r = sm.ld(region + j);

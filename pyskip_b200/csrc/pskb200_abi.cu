@@ -34,6 +34,8 @@ struct psk_store_s {
   uint32_t* d_vals = nullptr;
   cudaEvent_t ready = nullptr;  // async upload finished (waited on by the first consumer)
   cudaEvent_t busy = nullptr;   // async download finished (waited on before the memory is freed)
+  int32_t pending_slot = -1;    // result of psk_eval_async whose run count has not been read yet
+  int32_t failed = 0;           // status of a psk_eval_async that turned out to have failed
 };
 
 namespace {
@@ -59,6 +61,20 @@ struct Ctx {
   int stagger_ns = 0;
   unsigned long long* trace_buf = nullptr;  // PSK_PHASE_TIMING builds: device trace buffer
   int64_t trace_cap = 0, trace_tiles = 0;
+  // psk_eval_async: a ring of in-flight evaluations, each with its own pinned plan staging,
+  // pinned read-back words and completion event
+  static constexpr int kAsyncSlots = 32;
+  struct AsyncSlot {
+    cudaEvent_t done = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;  // bracket the merge kernel when profiling
+    bool timed = false;
+    int64_t runs_in = 0;
+    psk_store_s* owner = nullptr;
+  };
+  AsyncSlot slots[kAsyncSlots];
+  DPlan* h_plans = nullptr;     // [kAsyncSlots] pinned
+  int32_t* h_async = nullptr;   // [kAsyncSlots * 8] pinned
+  int next_slot = 0;
   DPlan* h_plan = nullptr;      // pinned staging copy of the plan
   int32_t* h_ctrl = nullptr;    // pinned read-back of CTRL words / small results
   std::atomic<int64_t> launches{0};
@@ -118,6 +134,14 @@ psk_status do_init(int device) {
   CUDA_TRY(cudaEventCreate(&g.pev0));
   CUDA_TRY(cudaEventCreate(&g.pev1));
   CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&g.h_plan), sizeof(DPlan)));
+  CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&g.h_plans), sizeof(DPlan) * Ctx::kAsyncSlots));
+  CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&g.h_async), sizeof(int32_t) * 8 * Ctx::kAsyncSlots));
+  for (int i = 0; i < Ctx::kAsyncSlots; ++i)
+  {
+    CUDA_TRY(cudaEventCreateWithFlags(&g.slots[i].done, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreate(&g.slots[i].t0));
+    CUDA_TRY(cudaEventCreate(&g.slots[i].t1));
+  }
   CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&g.h_ctrl), 64 * sizeof(int32_t)));
 #ifndef PSK_CPU_SIM
   cudaDeviceGetAttribute(&g.sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -167,7 +191,8 @@ psk_status new_store(int dtype, int64_t capacity, psk_store_t* out) {
   if (!s) return fail(PSK_ENOMEM, "out of host memory");
   s->dtype = dtype;
   s->capacity = capacity;
-  psk_status st = dmalloc(reinterpret_cast<void**>(&s->d_ends), (size_t)capacity * 4);
+  // one spare word behind the ends: k_merge_eval leaves the run count there
+  psk_status st = dmalloc(reinterpret_cast<void**>(&s->d_ends), (size_t)(capacity + 1) * 4);
   if (st == PSK_OK) st = dmalloc(reinterpret_cast<void**>(&s->d_vals), (size_t)capacity * 4);
   if (st != PSK_OK) {
     if (s->d_ends) cudaFreeAsync(s->d_ends, g.stream);
@@ -269,8 +294,9 @@ __global__ void k_validate_runs(const int32_t* ends, int32_t n, int32_t* flag) {
 }
 
 // (first payload, last payload, run count) of a store, as int64, for the stitch all-gather
-__global__ void k_boundary(const uint32_t* vals, int64_t nruns, long long* out3) {
+__global__ void k_boundary(const uint32_t* vals, int64_t nruns, const int32_t* d_count, long long* out3) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (d_count) nruns = *d_count;  // result of psk_eval_async: the count is still on the device
     out3[0] = (long long)vals[0];
     out3[1] = (long long)vals[nruns - 1];
     out3[2] = (long long)nruns;
@@ -342,6 +368,46 @@ psk_status encode_device(const void* d_dense, int64_t n, psk_store_t* out) {
 
 // ========================================================================================
 extern "C" {
+
+// Completes a store returned by psk_eval_async: waits for its kernels, reads the run count.
+psk_status resolve(psk_store_s* s) {
+  if (s->pending_slot >= 0) {
+    Ctx::AsyncSlot& slot = g.slots[s->pending_slot];
+    const int32_t* w = g.h_async + 8 * s->pending_slot;
+    cudaError_t e = cudaEventSynchronize(slot.done);
+    slot.owner = nullptr;
+    s->pending_slot = -1;
+    if (e != cudaSuccess) {
+      s->failed = PSK_ECUDA;
+    } else if (w[4] != 0) {
+      cudaMemsetAsync(g.d_async_err, 0, 4, g.stream);
+      s->failed = PSK_EINVAL;
+    } else if (w[CTRL_ERROR] != 0) {
+      s->failed = PSK_ESTATE;
+    } else {
+      s->nruns = w[CTRL_COUNT];
+      float ms = 0.f;
+      if (slot.timed && cudaEventElapsedTime(&ms, slot.t0, slot.t1) == cudaSuccess) {
+        g.prof_ms += ms;
+        g.prof_n += 1;
+        g.prof_runs_in += slot.runs_in;
+        g.prof_runs_out += s->nruns;
+      }
+    }
+    slot.timed = false;
+  }
+  if (s->failed == PSK_EINVAL)
+    return fail(PSK_EINVAL, "run ends of an asynchronously uploaded store are not positive and strictly increasing");
+  if (s->failed == PSK_ESTATE)
+    return fail(PSK_ESTATE, "psk_eval: tile capacity exceeded (internal partition bound violated)");
+  if (s->failed) return fail(PSK_ECUDA, "psk_eval_async: the evaluation failed on the device");
+  return PSK_OK;
+}
+#define READY(s)                             \
+  do {                                       \
+    psk_status r_ = resolve(s);              \
+    if (r_ != PSK_OK) return r_;             \
+  } while (0)
 
 const char* psk_last_error(void) { return g_err.c_str(); }
 const char* psk_version(void) { return "pskb200 0.1 (sm_100a)"; }
@@ -545,6 +611,7 @@ psk_status psk_store_from_runs_async(psk_dtype dtype, int64_t nruns, const int32
 psk_status psk_store_runs_async(psk_store_t s, int32_t* ends, void* vals) {
   NEED_INIT();
   PSK_CHECK_ARG(s != nullptr && ends != nullptr && vals != nullptr);
+  READY(s);
   PSK_CHECK_ARG(s->dtype == PSK_I32 || s->dtype == PSK_F32);
   const size_t n = (size_t)s->nruns;
   if (s->ready) CUDA_TRY(cudaStreamWaitEvent(g.d2h, s->ready, 0));
@@ -635,6 +702,7 @@ psk_status psk_store_from_dense(psk_dtype dtype, int64_t n, const void* dense, p
 psk_status psk_store_to_dense_device(psk_store_t s, void* d_out) {
   NEED_INIT();
   PSK_CHECK_ARG(s != nullptr && d_out != nullptr);
+  READY(s);
   const long long n = s->span;
   const unsigned nb = (unsigned)((n + kConvChunk - 1) / kConvChunk);
   switch (s->dtype) {
@@ -650,6 +718,7 @@ psk_status psk_store_to_dense_device(psk_store_t s, void* d_out) {
 psk_status psk_store_to_dense(psk_store_t s, void* out_host) {
   NEED_INIT();
   PSK_CHECK_ARG(s != nullptr && out_host != nullptr);
+  READY(s);
   void* d = nullptr;
   const size_t bytes = (size_t)s->span * elem_size(s->dtype);
   psk_status st = dmalloc(&d, bytes);
@@ -667,6 +736,7 @@ psk_status psk_store_to_dense(psk_store_t s, void* out_host) {
 psk_status psk_store_runs(psk_store_t s, int32_t* ends, void* vals) {
   NEED_INIT();
   PSK_CHECK_ARG(s != nullptr && ends != nullptr && vals != nullptr);
+  READY(s);
   const size_t n = (size_t)s->nruns;
   CUDA_TRY(cudaMemcpyAsync(ends, s->d_ends, n * 4, cudaMemcpyDeviceToHost, g.stream));
   if (elem_size(s->dtype) == 4) {
@@ -683,12 +753,23 @@ psk_status psk_store_runs(psk_store_t s, int32_t* ends, void* vals) {
   return PSK_OK;
 }
 
-int64_t psk_store_nruns(psk_store_t s) { return s ? s->nruns : 0; }
+int64_t psk_store_nruns(psk_store_t s) {
+  if (!s) return 0;
+  if (s->pending_slot >= 0 || s->failed) {
+    std::lock_guard<std::recursive_mutex> api_lock_(g.api_mu);
+    if (resolve(s) != PSK_OK) return -1;
+  }
+  return s->nruns;
+}
 int32_t psk_store_span(psk_store_t s) { return s ? s->span : 0; }
 int32_t psk_store_dtype(psk_store_t s) { return s ? s->dtype : -1; }
 
 psk_status psk_store_device_ptrs(psk_store_t s, const int32_t** d_ends, const uint32_t** d_vals) {
   PSK_CHECK_ARG(s != nullptr && d_ends != nullptr && d_vals != nullptr);
+  if (s->pending_slot >= 0 || s->failed) {
+    std::lock_guard<std::recursive_mutex> api_lock_(g.api_mu);
+    READY(s);
+  }
   *d_ends = s->d_ends;
   *d_vals = s->d_vals;
   return PSK_OK;
@@ -697,6 +778,7 @@ psk_status psk_store_device_ptrs(psk_store_t s, const int32_t** d_ends, const ui
 psk_status psk_store_first_value(psk_store_t s, uint32_t* bits) {
   NEED_INIT();
   PSK_CHECK_ARG(s != nullptr && bits != nullptr);
+  READY(s);
   CUDA_TRY(cudaMemcpyAsync(g.h_ctrl, s->d_vals, 4, cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   *bits = (uint32_t)g.h_ctrl[0];
@@ -706,6 +788,7 @@ psk_status psk_store_first_value(psk_store_t s, uint32_t* bits) {
 psk_status psk_store_boundary(psk_store_t s, uint32_t* first_bits, uint32_t* last_bits, int64_t* nruns) {
   NEED_INIT();
   PSK_CHECK_ARG(s != nullptr && first_bits != nullptr && last_bits != nullptr && nruns != nullptr);
+  READY(s);
   CUDA_TRY(cudaMemcpyAsync(g.h_ctrl, s->d_vals, 4, cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaMemcpyAsync(g.h_ctrl + 1, s->d_vals + (s->nruns - 1), 4, cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
@@ -718,7 +801,11 @@ psk_status psk_store_boundary(psk_store_t s, uint32_t* first_bits, uint32_t* las
 psk_status psk_store_boundary_device(psk_store_t s, int64_t* d_out3) {
   NEED_INIT();
   PSK_CHECK_ARG(s != nullptr && d_out3 != nullptr);
-  LAUNCH(k_boundary, 1, 32, 0, s->d_vals, (int64_t)s->nruns, reinterpret_cast<long long*>(d_out3));
+  // a deferred result is NOT completed here: the kernel reads its run count from the spare
+  // word behind the ends, so the caller's pipeline stays asynchronous
+  const int32_t* d_count = s->pending_slot >= 0 ? s->d_ends + s->capacity : nullptr;
+  if (!d_count) READY(s);
+  LAUNCH(k_boundary, 1, 32, 0, s->d_vals, (int64_t)s->nruns, d_count, reinterpret_cast<long long*>(d_out3));
   return PSK_OK;
 }
 
@@ -729,6 +816,10 @@ void psk_store_retain(psk_store_t s) {
 void psk_store_release(psk_store_t s) {
   if (!s) return;
   if (s->ref.fetch_sub(1) == 1) {
+    if (s->pending_slot >= 0) {  // result never looked at
+      std::lock_guard<std::recursive_mutex> api_lock_(g.api_mu);
+      g.slots[s->pending_slot].owner = nullptr;
+    }
     // stream-ordered free on the library stream, after any copy still reading / writing it
     if (s->ready) { cudaStreamWaitEvent(g.stream, s->ready, 0); cudaEventDestroy(s->ready); }
     if (s->busy) { cudaStreamWaitEvent(g.stream, s->busy, 0); cudaEventDestroy(s->busy); }
@@ -758,16 +849,31 @@ psk_status psk_view_span(int32_t span_in, int32_t nviews, const psk_view* views,
 }
 
 // ---- the hot path ----------------------------------------------------------------------
-psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const psk_node* prog,
-                    psk_dtype out_dtype, psk_eq eq, psk_store_t* out) {
-  NEED_INIT();
+namespace {
+psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const psk_node* prog,
+                     psk_dtype out_dtype, psk_eq eq, bool deferred, psk_store_t* out) {
   PSK_CHECK_ARG(out != nullptr && sources != nullptr && prog != nullptr);
   PSK_CHECK_ARG(k >= 1 && k <= PSK_MAX_SOURCES);  // lang.hpp:789-857
   PSK_CHECK_ARG(out_dtype >= PSK_I32 && out_dtype <= PSK_CHAR);
   psk_status st = validate_program(k, nprog, prog);
   if (st != PSK_OK) return st;
+  for (int i = 0; i < k; ++i) {
+    PSK_CHECK_ARG(sources[i].store != nullptr);
+    READY(sources[i].store);  // a source that is itself a deferred result: its run count is needed
+  }
+#ifdef PSK_PHASE_TIMING
+  deferred = false;
+#endif
+  // a deferred evaluation stages its plan and reads back its counters in its own ring slot
+  int slot = -1;
+  if (deferred) {
+    slot = g.next_slot;
+    g.next_slot = (g.next_slot + 1) % Ctx::kAsyncSlots;
+    if (g.slots[slot].owner) resolve(g.slots[slot].owner);  // ring full: finish the oldest
+    else cudaEventSynchronize(g.slots[slot].done);          // its owner was released unread
+  }
 
-  DPlan& hp = *g.h_plan;
+  DPlan& hp = deferred ? g.h_plans[slot] : *g.h_plan;
   hp.k = k;
   hp.eq = (eq == PSK_EQ_TYPED && out_dtype == PSK_F32) ? 1 : 0;
   hp.nprog = nprog;
@@ -895,7 +1001,7 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
     // persistent grid: as many CTAs as stay resident (shared memory / thread limits)
     int64_t grid = kCtasPerSm * (int64_t)g.sm_count;
     if (grid > max_tiles) grid = max_tiles;
-    if (g.profile) cudaEventRecord(g.pev0, g.stream);
+    if (g.profile) cudaEventRecord(deferred ? g.slots[slot].t0 : g.pev0, g.stream);
     bool launched = false;
 #ifndef PSK_CPU_SIM
     if (total_runs >= g.jit_min_runs) {
@@ -911,8 +1017,31 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
     }
 #endif
     if (!launched) launch_merge_eval(pick_K(k), (int)grid, d_plan);
-    if (g.profile) cudaEventRecord(g.pev1, g.stream);
+    if (g.profile) cudaEventRecord(deferred ? g.slots[slot].t1 : g.pev1, g.stream);
+    if (deferred) {
+      g.slots[slot].timed = g.profile;
+      g.slots[slot].runs_in = total_runs;
+    }
     e = cudaGetLastError();
+  }
+  if (deferred) {
+    int32_t* w = g.h_async + 8 * slot;
+    w[4] = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(w, hp.ctrl, CTRL_WORDS * 4, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess && used_async)
+      e = cudaMemcpyAsync(w + 4, g.d_async_err, 4, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaEventRecord(g.slots[slot].done, g.stream);
+    cudaFreeAsync(scratch, g.stream);
+    if (e != cudaSuccess) {
+      psk_store_release(res);
+      return fail(PSK_ECUDA, std::string("psk_eval_async: ") + cudaGetErrorString(e));
+    }
+    res->nruns = 0;  // known once the store is first used (resolve)
+    res->span = (int32_t)span;
+    res->pending_slot = slot;
+    g.slots[slot].owner = res;
+    *out = res;
+    return PSK_OK;
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(g.h_ctrl, hp.ctrl, CTRL_WORDS * 4, cudaMemcpyDeviceToHost, g.stream);
   g.h_ctrl[8] = 0;
@@ -956,6 +1085,19 @@ psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const p
   }
   *out = res;
   return PSK_OK;
+}
+}  // namespace
+
+psk_status psk_eval(int32_t k, const psk_source* sources, int32_t nprog, const psk_node* prog,
+                    psk_dtype out_dtype, psk_eq eq, psk_store_t* out) {
+  NEED_INIT();
+  return eval_impl(k, sources, nprog, prog, out_dtype, eq, false, out);
+}
+
+psk_status psk_eval_async(int32_t k, const psk_source* sources, int32_t nprog, const psk_node* prog,
+                          psk_dtype out_dtype, psk_eq eq, psk_store_t* out) {
+  NEED_INIT();
+  return eval_impl(k, sources, nprog, prog, out_dtype, eq, true, out);
 }
 
 // ---- masks -----------------------------------------------------------------------------
@@ -1008,6 +1150,7 @@ psk_status psk_mask_nd(int32_t ndim, const int32_t* shape, const int32_t* start,
 psk_status psk_reduce(psk_store_t s, psk_reduce_op op, uint64_t* result_bits) {
   NEED_INIT();
   PSK_CHECK_ARG(s != nullptr && result_bits != nullptr);
+  READY(s);
   PSK_CHECK_ARG(op >= PSK_RED_SUM && op <= PSK_RED_PROD);
   const bool is_f = s->dtype == PSK_F32;
   int nblocks = (int)((s->nruns + kRedThreads - 1) / kRedThreads);
@@ -1036,6 +1179,7 @@ psk_status psk_reduce(psk_store_t s, psk_reduce_op op, uint64_t* result_bits) {
 psk_status psk_store_slice(psk_store_t s, int32_t start, int32_t stop, psk_store_t* out) {
   NEED_INIT();
   PSK_CHECK_ARG(s != nullptr && out != nullptr);
+  READY(s);
   PSK_CHECK_ARG(0 <= start && start < stop && stop <= s->span);
   psk_source src;
   memset(&src, 0, sizeof(src));

@@ -198,6 +198,32 @@ def test_arg_errors(lib):
         lib.store_fill(A.I32, 0, 1)       # core.hpp:106 span > 0
 
 
+def test_eval_async_matches_sync(lib):
+    """psk_eval_async: results are fetched on first use; more evaluations in flight than ring
+    slots; a deferred result as the source of the next evaluation; a result released unread."""
+    from helpers import lower, to_abi_views
+    rng = np.random.default_rng(77)
+    n = 40_000
+    srcs = [rand_runs(rng, n, 900) + ([],) for _ in range(3)]
+    expr = ("add", ("mul", ("src", 0), ("src", 1)), ("src", 2))
+    want = oracle_eval(srcs, expr)
+    abi_prog, _, out_dt = lower(expr, [s[1].dtype for s in srcs])
+    stores = [(lib.store_from_runs(e, v), to_abi_views(vw)) for e, v, vw in srcs]
+    go = lib.prepare_eval(stores, abi_prog, A.DTYPE_OF_NP[out_dt], deferred=True)
+    results = [go() for _ in range(40)]          # > 32 outstanding: the oldest complete first
+    go()                                         # released without ever being looked at
+    for r in (results[0], results[17], results[-1]):
+        assert r.nruns == len(want[0])
+        assert_runs_equal(r.runs(), want, "deferred eval")
+    # chained: deferred result -> source of a deferred evaluation -> synchronous consumer
+    neg_prog, _, _ = lower(("neg", ("src", 0)), [np.dtype(np.int32)])
+    a = go()
+    b = lib.prepare_eval([(a, [])], neg_prog, A.I32, deferred=True)()
+    c = lib.eval([(b, [])], neg_prog, A.I32)
+    assert_runs_equal(c.runs(), want, "neg(neg(x))")
+    assert_runs_equal(b.runs(), (want[0], -want[1]), "neg(x)")
+
+
 @pytest.mark.gpu
 def test_jit_matches_interpreter_and_oracle():
     """The NVRTC-specialised kernel (large evaluations) and the generic interpreter kernel

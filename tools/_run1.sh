@@ -1,3 +1,3 @@
-timeout 900 python -m pytest tests/test_abi_eval.py tests/test_golden.py -m gpu -x -q 2>&1 | tail -3
-timeout 300 python tools/phase_profile.py --no-phase 2>&1 | grep -E "merge_eval avg|rror"
-timeout 300 python tools/phase_profile.py 2>&1 | tail -9
+BENCH_E2E_VERBOSE=1 timeout 300 python bench.py --steps 20 --warmup 3 2> gpurun_out/e2e_verbose.log | tail -1 > gpurun_out/bench_line.json
+timeout 300 python bench.py --steps 20 --warmup 3 2>/dev/null | tail -1 > gpurun_out/bench_line2.json
+nvidia-smi --query-gpu=pcie.link.gen.current,pcie.link.width.current --format=csv
