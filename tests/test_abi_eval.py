@@ -224,6 +224,32 @@ def test_eval_async_matches_sync(lib):
     assert_runs_equal(b.runs(), (want[0], -want[1]), "neg(x)")
 
 
+def test_boundary_of_deferred_result_stays_on_device(lib):
+    """psk_store_boundary_device on a psk_eval_async result does not complete it: the kernel
+    reads the run count from the spare word behind the ends (multi-GPU stitch, bench.py)."""
+    from helpers import lower, to_abi_views
+    rng = np.random.default_rng(78)
+    srcs = [rand_runs(rng, 30_000, 700) + ([],) for _ in range(2)]
+    expr = ("add", ("src", 0), ("src", 1))
+    we, wv = oracle_eval(srcs, expr)
+    abi_prog, _, out_dt = lower(expr, [s[1].dtype for s in srcs])
+    stores = [(lib.store_from_runs(e, v), to_abi_views(vw)) for e, v, vw in srcs]
+    res = lib.prepare_eval(stores, abi_prog, A.DTYPE_OF_NP[out_dt], deferred=True)()
+    if lib.is_simulator():
+        buf = np.zeros(3, np.int64)
+        lib.store_boundary_device(res, buf.ctypes.data)
+        got = buf
+    else:
+        import torch
+        buf = torch.zeros(3, dtype=torch.int64, device="cuda")
+        lib.store_boundary_device(res, buf.data_ptr())
+        lib.synchronize()
+        got = buf.cpu().numpy()
+    want = [int(np.uint32(np.int32(wv[0]))), int(np.uint32(np.int32(wv[-1]))), len(we)]
+    assert list(got) == want
+    assert lib.store_boundary(res) == tuple(want)        # completes the result; same answer
+
+
 @pytest.mark.gpu
 def test_jit_matches_interpreter_and_oracle():
     """The NVRTC-specialised kernel (large evaluations) and the generic interpreter kernel
