@@ -63,6 +63,10 @@ struct DPlan {
   unsigned long long* trace;       // [max_tiles * 8] per-tile globaltimer stamps (same builds)
   int32_t* out_ends;
   uint32_t* out_vals;
+  // single-tile evaluations (everything fits one tile, no views): the host writes the tile's
+  // bounds here and points `bounds` / `tile_hi` at them -- no partition kernels are launched
+  int32_t one_bounds[2 * PSK_MAX_SOURCES];
+  int32_t one_hi;
   psk_node prog[PSK_MAX_PROGRAM];
   DSource src[PSK_MAX_SOURCES];
 };

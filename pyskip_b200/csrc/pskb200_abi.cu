@@ -990,17 +990,32 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
   hp.out_vals = res->d_vals;
   hp.out_capacity = (int32_t)total_runs;
   DPlan* d_plan = reinterpret_cast<DPlan*>(scratch + o_plan);
+  // small evaluation without views: one tile holds every run (+ one look-ahead slot per source)
+  const bool single_tile = !any_views && total_runs + k <= kTileCap;
+  if (single_tile) {
+    for (int i = 0; i < k; ++i) {
+      hp.one_bounds[i] = 0;
+      hp.one_bounds[k + i] = hp.src[i].nruns;
+    }
+    hp.one_hi = (int32_t)span;
+    hp.n_tiles = 1;
+    hp.bounds = d_plan->one_bounds;   // device addresses inside the uploaded plan
+    hp.tile_hi = &d_plan->one_hi;
+  }
 
   cudaError_t e = cudaMemsetAsync(scratch, 0, o_merged, g.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_plan, &hp, plan_bytes, cudaMemcpyHostToDevice, g.stream);
   if (e == cudaSuccess) {
-    if (any_views) LAUNCH(k_prepare, 1, 32 * k, 0, d_plan);
-    LAUNCH(k_sample_keys, (unsigned)((max_samples + 255) / 256), 256, 0, d_plan);
-    LAUNCH(k_sample_rank, (unsigned)((max_samples + 255) / 256), 256, 0, d_plan);
-    LAUNCH(k_tile_bounds, (unsigned)(((max_tiles + 1) * k + 255) / 256), 256, 0, d_plan);
+    if (!single_tile) {
+      if (any_views) LAUNCH(k_prepare, 1, 32 * k, 0, d_plan);
+      LAUNCH(k_sample_keys, (unsigned)((max_samples + 255) / 256), 256, 0, d_plan);
+      LAUNCH(k_sample_rank, (unsigned)((max_samples + 255) / 256), 256, 0, d_plan);
+      LAUNCH(k_tile_bounds, (unsigned)(((max_tiles + 1) * k + 255) / 256), 256, 0, d_plan);
+    }
     // persistent grid: as many CTAs as stay resident (shared memory / thread limits)
     int64_t grid = kCtasPerSm * (int64_t)g.sm_count;
     if (grid > max_tiles) grid = max_tiles;
+    if (single_tile) grid = 1;
     if (g.profile) cudaEventRecord(deferred ? g.slots[slot].t0 : g.pev0, g.stream);
     bool launched = false;
 #ifndef PSK_CPU_SIM

@@ -204,7 +204,7 @@ def test_eval_async_matches_sync(lib):
     from helpers import lower, to_abi_views
     rng = np.random.default_rng(77)
     n = 40_000
-    srcs = [rand_runs(rng, n, 900) + ([],) for _ in range(3)]
+    srcs = [rand_runs(rng, n, 4000) + ([],) for _ in range(3)]   # > one tile
     expr = ("add", ("mul", ("src", 0), ("src", 1)), ("src", 2))
     want = oracle_eval(srcs, expr)
     abi_prog, _, out_dt = lower(expr, [s[1].dtype for s in srcs])
