@@ -127,8 +127,7 @@ PSK_D int32_t warp_bound_mapped(const DSource& s, int32_t lo, int32_t hi, int32_
 // ---------------------------------------------------------------------------------------
 // k_prepare: one warp per source.  [a, e) = runs whose mapped end is in (0, span], cut
 // after the first run that reaches span (everything later is a zero-length mapped run).
-__global__ void k_prepare(DPlan* p) {
-  __shared__ int32_t s_ns[PSK_MAX_SOURCES];
+PSK_D void prepare_body(DPlan* p, int32_t* s_ns /*[PSK_MAX_SOURCES] shared*/) {
   const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = p->k;
   if (i < k) {
@@ -159,6 +158,10 @@ __global__ void k_prepare(DPlan* p) {
     p->n_tiles = nt < 1 ? 1 : nt;
   }
 }
+__global__ void k_prepare(DPlan* p) {
+  __shared__ int32_t s_ns[PSK_MAX_SOURCES];
+  prepare_body(p, s_ns);
+}
 
 PSK_D int32_t sample_key(const DSource& s, int32_t j, int32_t S) {
   int32_t n = s.e - s.a;
@@ -181,31 +184,23 @@ PSK_D int sample_owner(const int32_t* s_off, int k, int32_t sid) {
 // ---------------------------------------------------------------------------------------
 // k_sample_keys: samp_keys[sid] = mapped end of sample sid.  The view chain of a source is
 // evaluated once per sample here, never inside the ranking searches.
+PSK_D void sample_key_body(DPlan* p, int32_t sid, const int32_t* s_off, int k) {
+  const int i = sample_owner(s_off, k, sid);
+  p->samp_keys[sid] = sample_key(p->src[i], sid - s_off[i], p->S);
+}
 __global__ void k_sample_keys(DPlan* p) {
   __shared__ int32_t s_off[PSK_MAX_SOURCES];
   const int k = p->k;
   if ((int)threadIdx.x < k) s_off[threadIdx.x] = p->src[threadIdx.x].samp_off;
   __syncthreads();
   const int32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (sid >= p->total_samples) return;
-  const int i = sample_owner(s_off, k, sid);
-  p->samp_keys[sid] = sample_key(p->src[i], sid - s_off[i], p->S);
+  if (sid < p->total_samples) sample_key_body(p, sid, s_off, k);
 }
 
 // ---------------------------------------------------------------------------------------
 // k_sample_rank: merged[rank] = key, where rank orders all samples by (key, source, index):
 // own index + one binary search over the sample keys of every other source.
-__global__ void k_sample_rank(DPlan* p) {
-  __shared__ int32_t s_off[PSK_MAX_SOURCES];
-  __shared__ int32_t s_ns[PSK_MAX_SOURCES];
-  const int k = p->k;
-  if ((int)threadIdx.x < k) {
-    s_off[threadIdx.x] = p->src[threadIdx.x].samp_off;
-    s_ns[threadIdx.x] = p->src[threadIdx.x].ns;
-  }
-  __syncthreads();
-  const int32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (sid >= p->total_samples) return;
+PSK_D void sample_rank_body(DPlan* p, int32_t sid, const int32_t* s_off, const int32_t* s_ns, int k) {
   const int32_t* const keys = p->samp_keys;
   const int i = sample_owner(s_off, k, sid);
   const int32_t key = keys[sid];
@@ -241,15 +236,25 @@ __global__ void k_sample_rank(DPlan* p) {
   }
   p->merged[rank] = key;
 }
+__global__ void k_sample_rank(DPlan* p) {
+  __shared__ int32_t s_off[PSK_MAX_SOURCES];
+  __shared__ int32_t s_ns[PSK_MAX_SOURCES];
+  const int k = p->k;
+  if ((int)threadIdx.x < k) {
+    s_off[threadIdx.x] = p->src[threadIdx.x].samp_off;
+    s_ns[threadIdx.x] = p->src[threadIdx.x].ns;
+  }
+  __syncthreads();
+  const int32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sid < p->total_samples) sample_rank_body(p, sid, s_off, s_ns, k);
+}
 
 // ---------------------------------------------------------------------------------------
 // k_tile_bounds: bounds[t][i] = first run of source i whose mapped end is > hi(t-1).  The
 // source's own sample keys narrow the search to one sample interval (<= S runs) before any
 // run end is loaded or mapped.
-__global__ void k_tile_bounds(DPlan* p) {
-  int32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+PSK_D void tile_bound_body(DPlan* p, int32_t id) {
   const int k = p->k, nt = p->n_tiles, m = p->m;
-  if (id >= (nt + 1) * k) return;
   int32_t t = id / k, i = id - t * k;
   const DSource& s = p->src[i];
   int32_t b;
@@ -277,6 +282,35 @@ __global__ void k_tile_bounds(DPlan* p) {
   }
   p->bounds[t * k + i] = b;
   if (i == 0 && t > 0) p->tile_hi[t - 1] = (t == nt) ? p->span : p->merged[t * m - 1];
+}
+__global__ void k_tile_bounds(DPlan* p) {
+  const int32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id < (p->n_tiles + 1) * p->k) tile_bound_body(p, id);
+}
+
+// ---------------------------------------------------------------------------------------
+// k_partition_small: the four kernels above as ONE block for evaluations with few samples
+// (three launches and their dependency gaps cost more than the work).
+__global__ void k_partition_small(DPlan* p, int do_prepare) {
+  __shared__ int32_t s_off[PSK_MAX_SOURCES];
+  __shared__ int32_t s_ns[PSK_MAX_SOURCES];
+  const int k = p->k;
+  if (do_prepare) {
+    prepare_body(p, s_ns);
+    __syncthreads();
+  }
+  if ((int)threadIdx.x < k) {
+    s_off[threadIdx.x] = p->src[threadIdx.x].samp_off;
+    s_ns[threadIdx.x] = p->src[threadIdx.x].ns;
+  }
+  __syncthreads();
+  const int32_t total = p->total_samples;
+  for (int32_t sid = threadIdx.x; sid < total; sid += blockDim.x) sample_key_body(p, sid, s_off, k);
+  __syncthreads();
+  for (int32_t sid = threadIdx.x; sid < total; sid += blockDim.x) sample_rank_body(p, sid, s_off, s_ns, k);
+  __syncthreads();
+  const int32_t nb = (p->n_tiles + 1) * k;
+  for (int32_t id = threadIdx.x; id < nb; id += blockDim.x) tile_bound_body(p, id);
 }
 
 // ---------------------------------------------------------------------------------------

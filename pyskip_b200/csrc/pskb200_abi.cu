@@ -850,6 +850,8 @@ psk_status psk_view_span(int32_t span_in, int32_t nviews, const psk_view* views,
 
 // ---- the hot path ----------------------------------------------------------------------
 namespace {
+constexpr int64_t kSmallPartition = 2048;  // samples up to which one block does the whole partition
+
 psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const psk_node* prog,
                      psk_dtype out_dtype, psk_eq eq, bool deferred, psk_store_t* out) {
   PSK_CHECK_ARG(out != nullptr && sources != nullptr && prog != nullptr);
@@ -1006,7 +1008,10 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
   cudaError_t e = cudaMemsetAsync(scratch, 0, o_merged, g.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_plan, &hp, plan_bytes, cudaMemcpyHostToDevice, g.stream);
   if (e == cudaSuccess) {
-    if (!single_tile) {
+    if (!single_tile && max_samples <= kSmallPartition) {
+      // few samples: prepare + keys + rank + bounds in one block
+      LAUNCH(k_partition_small, 1, 1024, 0, d_plan, any_views ? 1 : 0);
+    } else if (!single_tile) {
       if (any_views) LAUNCH(k_prepare, 1, 32 * k, 0, d_plan);
       LAUNCH(k_sample_keys, (unsigned)((max_samples + 255) / 256), 256, 0, d_plan);
       LAUNCH(k_sample_rank, (unsigned)((max_samples + 255) / 256), 256, 0, d_plan);
