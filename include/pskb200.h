@@ -169,6 +169,11 @@ PSK_API int64_t psk_live_bytes(void);
  * their program at run time (NVRTC; the generic interpreter kernel otherwise or when NVRTC
  * is unavailable).  Negative: never.  Default 2^18. */
 PSK_API psk_status psk_set_jit_threshold(int64_t min_total_runs);
+/* Evaluations with at most `max_samples` partition samples run their whole partition step
+ * (sample keys, ranking, tile bounds) as one thread block instead of three grid launches,
+ * and evaluations that fit one tile skip it altogether.  0: always take the grid path (the
+ * tests use this to drive the large-input kernels with small inputs).  Default 2048. */
+PSK_API psk_status psk_set_small_partition(int64_t max_samples);
 /* NVRTC stage of the specialisation only (needs no GPU): 0 when the kernel specialised for
  * `prog` over k sources compiles to an sm_100a cubin; the compiler log goes to `log`. */
 PSK_API int32_t psk_jit_compile_check(int32_t k, int32_t nprog, const psk_node* prog, char* log,

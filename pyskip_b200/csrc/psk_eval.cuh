@@ -236,17 +236,91 @@ PSK_D void sample_rank_body(DPlan* p, int32_t sid, const int32_t* s_off, const i
   }
   p->merged[rank] = key;
 }
+// Block-cooperative form for large evaluations.  The 256 samples of a block are (nearly
+// always) consecutive samples of one source, so their ranks in another source q fall into a
+// short window of q's keys: two threads locate the window in global memory, the block loads
+// it into shared memory (coalesced) and every thread searches there.  The per-thread global
+// searches of sample_rank_body cost one 32-byte sector per probe and lane once the lanes'
+// paths diverge (~120 MB of L2 traffic at config 2); this form reads each key about once.
+constexpr int kRankBlock = 256;
+constexpr int kRankWindow = 1024;
 __global__ void k_sample_rank(DPlan* p) {
   __shared__ int32_t s_off[PSK_MAX_SOURCES];
   __shared__ int32_t s_ns[PSK_MAX_SOURCES];
-  const int k = p->k;
-  if ((int)threadIdx.x < k) {
-    s_off[threadIdx.x] = p->src[threadIdx.x].samp_off;
-    s_ns[threadIdx.x] = p->src[threadIdx.x].ns;
+  __shared__ int32_t s_wlo[PSK_MAX_SOURCES];
+  __shared__ int32_t s_whi[PSK_MAX_SOURCES];
+  __shared__ int32_t s_win[kRankWindow];
+  __shared__ int32_t s_min[kRankBlock / 32], s_max[kRankBlock / 32];
+  const int k = p->k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < k) {
+    s_off[tid] = p->src[tid].samp_off;
+    s_ns[tid] = p->src[tid].ns;
   }
   __syncthreads();
-  const int32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (sid < p->total_samples) sample_rank_body(p, sid, s_off, s_ns, k);
+  const int32_t* const keys = p->samp_keys;
+  const int32_t total = p->total_samples;
+  const int32_t sid = blockIdx.x * kRankBlock + tid;
+  const bool valid = sid < total;
+  const int32_t key = valid ? keys[sid] : 0;
+  const int i = valid ? sample_owner(s_off, k, sid) : 0;
+  // smallest / largest key of the block
+  int32_t kmin = valid ? key : kSentinel, kmax = valid ? key : -1;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    kmin = imin(kmin, __shfl_xor_sync(0xffffffffu, kmin, d));
+    kmax = imax(kmax, __shfl_xor_sync(0xffffffffu, kmax, d));
+  }
+  if (lane == 0) {
+    s_min[warp] = kmin;
+    s_max[warp] = kmax;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < kRankBlock / 32; ++w) {
+    kmin = imin(kmin, s_min[w]);
+    kmax = imax(kmax, s_max[w]);
+  }
+  // window of every source: [#keys < kmin, #keys <= kmax)
+  if (tid < 2 * k) {
+    const int q = tid >> 1;
+    const bool upper = (tid & 1) != 0;
+    const int32_t* const kq = keys + s_off[q];
+    int32_t lo = 0, hi = s_ns[q];
+    while (lo < hi) {
+      const int32_t mid = lo + ((hi - lo) >> 1);
+      const int32_t v = kq[mid];
+      if (upper ? (v <= kmax) : (v < kmin)) lo = mid + 1; else hi = mid;
+    }
+    if (upper) s_whi[q] = lo; else s_wlo[q] = lo;
+  }
+  __syncthreads();
+  int32_t rank = valid ? sid - s_off[i] : 0;
+  for (int q = 0; q < k; ++q) {
+    const int32_t wlo = s_wlo[q], w = s_whi[q] - wlo;  // uniform over the block
+    const int32_t* const kq = keys + s_off[q] + wlo;
+    const bool mine = valid && q != i;
+    int32_t lo = 0, hi = w;
+    if (w <= kRankWindow) {
+      for (int32_t t = tid; t < w; t += kRankBlock) s_win[t] = kq[t];
+      __syncthreads();
+      if (mine) {
+        while (lo < hi) {
+          const int32_t mid = lo + ((hi - lo) >> 1);
+          const int32_t v = s_win[mid];
+          if ((q < i) ? (v <= key) : (v < key)) lo = mid + 1; else hi = mid;
+        }
+      }
+      __syncthreads();
+    } else if (mine) {  // skewed sources: search the window in global memory
+      while (lo < hi) {
+        const int32_t mid = lo + ((hi - lo) >> 1);
+        const int32_t v = kq[mid];
+        if ((q < i) ? (v <= key) : (v < key)) lo = mid + 1; else hi = mid;
+      }
+    }
+    if (mine) rank += wlo + lo;
+  }
+  if (valid) p->merged[rank] = key;
 }
 
 // ---------------------------------------------------------------------------------------

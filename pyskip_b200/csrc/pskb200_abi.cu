@@ -58,6 +58,7 @@ struct Ctx {
   unsigned long long phase_cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int64_t jit_min_runs = 1 << 18;  // evaluations at least this large get a specialised kernel
   int64_t jit_launches = 0;
+  int64_t small_partition = 2048;  // samples up to which one block does the whole partition
   int stagger_ns = 0;
   unsigned long long* trace_buf = nullptr;  // PSK_PHASE_TIMING builds: device trace buffer
   int64_t trace_cap = 0, trace_tiles = 0;
@@ -481,6 +482,12 @@ int64_t psk_launch_count(int32_t reset) {
 
 int64_t psk_live_bytes(void) { return g.live_bytes.load(); }
 
+psk_status psk_set_small_partition(int64_t max_samples) {
+  std::lock_guard<std::recursive_mutex> api_lock_(g.api_mu);
+  g.small_partition = max_samples < 0 ? 0 : max_samples;
+  return PSK_OK;
+}
+
 psk_status psk_set_jit_threshold(int64_t min_total_runs) {
   g.jit_min_runs = min_total_runs;
   return PSK_OK;
@@ -850,7 +857,6 @@ psk_status psk_view_span(int32_t span_in, int32_t nviews, const psk_view* views,
 
 // ---- the hot path ----------------------------------------------------------------------
 namespace {
-constexpr int64_t kSmallPartition = 2048;  // samples up to which one block does the whole partition
 
 psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const psk_node* prog,
                      psk_dtype out_dtype, psk_eq eq, bool deferred, psk_store_t* out) {
@@ -993,7 +999,7 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
   hp.out_capacity = (int32_t)total_runs;
   DPlan* d_plan = reinterpret_cast<DPlan*>(scratch + o_plan);
   // small evaluation without views: one tile holds every run (+ one look-ahead slot per source)
-  const bool single_tile = !any_views && total_runs + k <= kTileCap;
+  const bool single_tile = !any_views && total_runs + k <= kTileCap && g.small_partition > 0;
   if (single_tile) {
     for (int i = 0; i < k; ++i) {
       hp.one_bounds[i] = 0;
@@ -1008,13 +1014,13 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
   cudaError_t e = cudaMemsetAsync(scratch, 0, o_merged, g.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_plan, &hp, plan_bytes, cudaMemcpyHostToDevice, g.stream);
   if (e == cudaSuccess) {
-    if (!single_tile && max_samples <= kSmallPartition) {
+    if (!single_tile && max_samples <= g.small_partition) {
       // few samples: prepare + keys + rank + bounds in one block
       LAUNCH(k_partition_small, 1, 1024, 0, d_plan, any_views ? 1 : 0);
     } else if (!single_tile) {
       if (any_views) LAUNCH(k_prepare, 1, 32 * k, 0, d_plan);
       LAUNCH(k_sample_keys, (unsigned)((max_samples + 255) / 256), 256, 0, d_plan);
-      LAUNCH(k_sample_rank, (unsigned)((max_samples + 255) / 256), 256, 0, d_plan);
+      LAUNCH(k_sample_rank, (unsigned)((max_samples + kRankBlock - 1) / kRankBlock), kRankBlock, 0, d_plan);
       LAUNCH(k_tile_bounds, (unsigned)(((max_tiles + 1) * k + 255) / 256), 256, 0, d_plan);
     }
     // persistent grid: as many CTAs as stay resident (shared memory / thread limits)

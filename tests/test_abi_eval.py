@@ -224,6 +224,35 @@ def test_eval_async_matches_sync(lib):
     assert_runs_equal(b.runs(), (want[0], -want[1]), "neg(x)")
 
 
+def test_grid_partition_kernels_on_small_inputs(lib):
+    """The large-input partition kernels (k_sample_keys / block-cooperative k_sample_rank /
+    k_tile_bounds) driven with small inputs: equal densities, a 50x skew between sources (the
+    rank windows overflow shared memory and fall back to global searches), views, ties."""
+    rng = np.random.default_rng(79)
+    try:
+        lib.set_small_partition(0)
+        span = 200_000
+        for trial, counts in enumerate([(3000, 3000, 3000), (12_000, 240, 5), (1, 9000, 1), (40_000, 10), (4000, 4000)]):
+            srcs = [rand_runs(rng, span, c) + ([],) for c in counts]
+            e = ("src", 0)
+            for i in range(1, len(srcs)):
+                e = ("add", e, ("mul", ("src", i), ("const", i + 2, np.int32)))
+            assert_runs_equal(run_eval(lib, srcs, e), oracle_eval(srcs, e), f"grid partition {trial}")
+        # shared ends everywhere (ties across all sources) + a strided view
+        base = rand_runs(rng, span, 5000)
+        srcs = [(base[0], base[1] + j, []) for j in range(4)]
+        e = ("max", ("add", ("src", 0), ("src", 1)), ("sub", ("src", 2), ("src", 3)))
+        assert_runs_equal(run_eval(lib, srcs, e), oracle_eval(srcs, e), "ties")
+        big = rand_runs(rng, span, 6000)
+        view = [("gather", (span,), [(10, span - 10, 2)])]       # every 2nd element of [10, span - 10)
+        other = rand_runs(rng, (span - 20 + 1) // 2, 700)
+        srcs = [big + (view,), other + ([],)]
+        e = ("sub", ("src", 0), ("src", 1))
+        assert_runs_equal(run_eval(lib, srcs, e), oracle_eval(srcs, e), "view")
+    finally:
+        lib.set_small_partition(2048)
+
+
 def test_boundary_of_deferred_result_stays_on_device(lib):
     """psk_store_boundary_device on a psk_eval_async result does not complete it: the kernel
     reads the run count from the spare word behind the ends (multi-GPU stitch, bench.py)."""
