@@ -10,20 +10,24 @@
 // B200 design:
 //   k_prepare      (only with views) trims every source to the run range that can reach the
 //                  output -- the role of lang::make_pool's slice_invert calls (lang.hpp:708-709).
-//   k_sample_rank  takes every S-th mapped run end of every source and ranks it among all
-//                  samples (k binary searches): a sorted splitter list balanced by RUN COUNT,
-//                  not by coordinate (the reference's TODO at eval.hpp:450-451).
-//   k_tile_bounds  every m-th splitter closes a tile; one binary search per (tile, source)
-//                  gives the tile's run slice.  A tile holds <= (m + 2k) * S runs, so it
-//                  always fits in shared memory.
-//   k_merge_eval   persistent CTAs take tiles in order (atomic ticket), stage the tile's
-//                  run slices in shared memory (coalesced loads, views applied on the fly,
-//                  zero-length mapped runs dropped), split the tile's coordinate range over
-//                  the threads, and every thread runs the sequential k-way merge over its
-//                  sub-range with the heads of all sources in registers.  A span is kept iff
-//                  its value differs from the NEXT span's value (the later value wins, as
-//                  in eval.hpp:189-202), which is a thread-local decision, so compaction is a
-//                  block scan plus a decoupled look-back across tiles -- one pass over HBM.
+//   k_sample_keys  mapped end of every S-th run of every source (the view chain is evaluated
+//                  once per sample).
+//   k_sample_rank  ranks every sample among all samples: a sorted splitter list balanced by
+//                  RUN COUNT, not by coordinate (the reference's TODO at eval.hpp:450-451).
+//   k_tile_bounds  every m-th splitter closes a tile; per (tile, source) a search over the
+//                  source's sample keys, then inside one sample interval.  A tile holds
+//                  <= (m + 2k) * S runs, so it always fits in shared memory.
+//   k_partition_small  the four steps above as one block for evaluations with few samples.
+//   k_merge_eval   persistent CTAs take tiles in order (atomic ticket).  The tile's raw runs
+//                  arrive from registers (loaded one tile earlier, in four bursts) into flat
+//                  shared-memory slots; with views the ends are mapped and zero-length mapped
+//                  runs squeezed out in place; the tile's coordinate range is split over the
+//                  threads (coarse-to-fine cursor search) and every thread merges its slice
+//                  sequentially with the heads of all sources in registers, one distinct end
+//                  per iteration.  A span is kept iff its value differs from the NEXT span's
+//                  value (the later value wins, as in eval.hpp:189-202), which is a
+//                  thread-local decision, so compaction is a block scan plus a decoupled
+//                  look-back across tiles (deferred by one tile) -- one pass over HBM.
 #pragma once
 
 #include "psk_ops.h"
@@ -522,8 +526,8 @@ struct InterpEval {
 // k_merge_eval<K>: K = compile-time bound on the number of sources (heads live in registers).
 //
 // Shared memory per CTA: in[] = the tile's runs as (end, value) pairs, one slice per source
-// plus one look-ahead run each; out[] = the spans each thread keeps.  After the block scan
-// in[] is dead and becomes the compacted staging area for the coalesced global write.
+// plus one look-ahead run each; out[] = the spans each thread keeps; pend[] = the compacted
+// spans of the previous tile, parked until their global offset is known (one tile later).
 struct TileDesc {          // bounds of one tile, fetched one tile ahead
   int32_t tile;
   int32_t lo, hi;
