@@ -225,9 +225,6 @@ bool compile_cubin(int K, bool typed_float, bool views, int nprog, const psk_nod
 #ifdef PSK_COARSE_SEARCH
                         "-DPSK_COARSE_SEARCH=" PSK_STR(PSK_COARSE_SEARCH),
 #endif
-#ifdef PSK_LOOKBACK_WARP
-                        "-DPSK_LOOKBACK_WARP",
-#endif
   };
   r = g_api.nvrtcCompileProgram(np, (int)(sizeof(opts) / sizeof(opts[0])), opts);
   if (r != 0) {
