@@ -82,3 +82,29 @@ def test_random_programs_views_and_partitions(lib, seed):
                                          f"views={[s[2] for s in srcs]}")
     finally:
         lib.set_small_partition(2048)
+
+
+@pytest.mark.gpu
+def test_random_programs_through_the_specialised_kernel():
+    """The same generator with every evaluation forced onto the NVRTC-specialised kernel
+    (exact k, compile-time equality mode and view handling)."""
+    from helpers import cuda_lib
+    lib = cuda_lib()
+    rng = np.random.default_rng(9900)
+    try:
+        lib.set_jit_threshold(0)
+        before = lib.jit_launch_count()
+        for trial in range(6):
+            dtype = np.float32 if trial % 2 else np.int32
+            w, h = int(rng.integers(20, 90)), int(rng.integers(10, 60))
+            k = int(rng.integers(2, 6))
+            srcs = [_source(rng, w, h, dtype) for _ in range(k)]
+            ops = FLT_OPS if dtype == np.float32 else INT_OPS
+            e = ("src", 0)
+            for i in range(1, k):
+                e = (str(rng.choice(ops)), e, ("src", i))
+            eq = "typed" if trial % 3 == 0 else "bitwise"
+            assert_runs_equal(run_eval(lib, srcs, e, eq), oracle_eval(srcs, e, eq), f"jit trial {trial}")
+        assert lib.jit_launch_count() - before == 6
+    finally:
+        lib.set_jit_threshold(1 << 18)
