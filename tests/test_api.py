@@ -191,6 +191,29 @@ def test_wide_expression_is_cut_correctly(api):
     assert np.array_equal(got, np.sum(arrs, axis=0).astype(np.int32))
 
 
+def test_sources_per_launch_does_not_change_results(api):
+    """gpu_eval_max_sources only decides how a wide expression is chained into launches: the
+    association order, and with it every float result, stays the reference's left-to-right
+    one -- bit for bit, whatever the width."""
+    ps, _ = api
+    rng = np.random.default_rng(10)
+    arrs = [(rng.integers(0, 4, 600) * np.float32(0.1)).astype(np.float32) for _ in range(27)]
+    wts = [np.float32(0.3 + 0.07 * i) for i in range(27)]
+    want = np.zeros(600, np.float32)
+    for a, w in zip(arrs, wts):                       # float32, left to right, mul and add rounded separately
+        want = (want + (a * w).astype(np.float32)).astype(np.float32)
+    outs = []
+    for width in (2, 5, 8, 30):
+        with ps.config.config_scope(gpu_eval_max_sources=width):
+            with ps.config.lazy_evaluation_scope():
+                acc = ps.Tensor(shape=(600,), dtype=float, val=0.0)
+                for a, w in zip(arrs, wts):
+                    acc = acc + ps.Tensor.from_numpy(a) * float(w)
+                outs.append(acc.to_numpy())
+    for o in outs:
+        assert np.array_equal(o.view(np.uint32), want.view(np.uint32))
+
+
 def test_conv3d_matches_dense_oracle(api):
     ps, E = api
     big = E._backend_is_simulator() == 0
