@@ -42,7 +42,7 @@ struct Expr {
   int32_t span = 0;      // output length (ExprData::span, lang.hpp:100)
   int size = 1;          // node count of the subtree as a tree (ExprData::size, lang.hpp:99)
   // STORE
-  StoreRef store;
+  mutable StoreRef store;      // a constant's device store is only created when something needs it
   bool is_const = false;       // 1-run store: value known on the host
   uint32_t const_bits = 0;
   // VIEW
@@ -62,13 +62,28 @@ inline ExprPtr make_store_expr(StoreRef store, int dtype) {
   return e;
 }
 
+// A filled array (broadcast scalar, macros.hpp:16-23; Array(span, fill), array.hpp:82-84) is a
+// constant of the expression language: it lowers to an immediate of the fused program, so its
+// 1-run device store is created lazily (expr_store) -- most scalars never need one.
 inline ExprPtr make_fill_expr(int dtype, int32_t span, uint32_t bits) {
-  psk_store_t h = nullptr;
-  check(backend().psk_store_fill((psk_dtype)dtype, span, bits, &h));
-  auto e = make_store_expr(StoreRef(h), dtype);
+  PSK_CHECK_ARGUMENT(span > 0);
+  auto e = std::make_shared<Expr>();
+  e->kind = Expr::STORE;
+  e->dtype = dtype;
+  e->span = span;
   e->is_const = true;
   e->const_bits = bits;
   return e;
+}
+
+// the device store of a STORE node
+inline const StoreRef& expr_store(const Expr* e) {
+  if (!e->store && e->is_const) {
+    psk_store_t h = nullptr;
+    check(backend().psk_store_fill((psk_dtype)e->dtype, e->span, e->const_bits, &h));
+    e->store = StoreRef(h);
+  }
+  return e->store;
 }
 
 inline int32_t view_out_span(int32_t span_in, const psk_view& v) {
@@ -339,14 +354,14 @@ inline StoreRef materialize_typed(const ExprPtr& e) {
   // A bare store still takes the final pass in the reference (normalize wraps it in a slice,
   // lang.hpp:532-540).  For int/bool/char both equalities coincide and a store is already
   // canonical, so only multi-run float stores need it (-0/+0, NaN: SURVEY.md A.2).
-  if (e->kind == Expr::STORE && (e->is_const || e->dtype != PSK_F32)) return e->store;
+  if (e->kind == Expr::STORE && (e->is_const || e->dtype != PSK_F32)) return expr_store(e.get());
   Planner p;
   return p.materialize(e, PSK_EQ_TYPED);
 }
 
 // lang::evaluate (lang.hpp:902-905): Box-typed (BITWISE) materialisation
 inline StoreRef materialize_bitwise(const ExprPtr& e) {
-  if (e->kind == Expr::STORE && (e->is_const || e->dtype != PSK_F32)) return e->store;
+  if (e->kind == Expr::STORE && (e->is_const || e->dtype != PSK_F32)) return expr_store(e.get());
   Planner p;
   return p.materialize(e, PSK_EQ_BITWISE);
 }
