@@ -104,7 +104,7 @@ def make_view(kind, shape, comps=None, scale=None, offset=None) -> View:
 _SYMBOLS = [
     "psk_last_error", "psk_version", "psk_is_simulator", "psk_init", "psk_device_count",
     "psk_synchronize", "psk_get_stream", "psk_set_stream", "psk_timer_start", "psk_timer_stop", "psk_launch_count",
-    "psk_live_bytes", "psk_profile", "psk_profile_read", "psk_set_jit_threshold", "psk_set_small_partition", "psk_jit_launch_count", "psk_jit_compile_check", "psk_store_from_runs", "psk_store_from_runs_async", "psk_store_runs_async", "psk_copy_synchronize", "psk_store_from_device_runs", "psk_store_fill",
+    "psk_live_bytes", "psk_profile", "psk_profile_read", "psk_set_jit_threshold", "psk_set_small_partition", "psk_set_vector_conversion", "psk_jit_launch_count", "psk_jit_compile_check", "psk_store_from_runs", "psk_store_from_runs_async", "psk_store_runs_async", "psk_copy_synchronize", "psk_store_from_device_runs", "psk_store_fill",
     "psk_store_from_dense", "psk_store_from_dense_device", "psk_store_to_dense",
     "psk_store_to_dense_device", "psk_store_runs", "psk_store_nruns", "psk_store_span",
     "psk_store_dtype", "psk_store_device_ptrs", "psk_store_first_value", "psk_eval_async", "psk_store_retain",
@@ -183,6 +183,7 @@ class Lib:
         c.psk_jit_launch_count.restype = C.c_int64
         c.psk_set_jit_threshold.argtypes = [C.c_int64]
         c.psk_set_small_partition.argtypes = [C.c_int64]
+        c.psk_set_vector_conversion.argtypes = [C.c_int32]
         c.psk_store_nruns.restype = C.c_int64
         c.psk_store_nruns.argtypes = [C.c_void_p]
         c.psk_store_span.argtypes = [C.c_void_p]
@@ -257,6 +258,9 @@ class Lib:
 
     def set_jit_threshold(self, min_total_runs: int):
         self._chk(self.c.psk_set_jit_threshold(C.c_int64(min_total_runs)))
+
+    def set_vector_conversion(self, enable: bool):
+        self._chk(self.c.psk_set_vector_conversion(1 if enable else 0))
 
     def set_small_partition(self, max_samples: int):
         self._chk(self.c.psk_set_small_partition(C.c_int64(max_samples)))

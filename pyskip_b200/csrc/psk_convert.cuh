@@ -139,6 +139,167 @@ __global__ void __launch_bounds__(kConvThreads) k_encode_write(const void* dense
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Vectorised forms for 4-byte element types and 16-byte aligned dense buffers
+// (selected at run time by psk_set_vector_conversion; off by default until measured on the
+// GPU -- the scalar kernels above reach 12-19 % of the HBM peak, profiles/r1_summary.md).
+// Every thread moves 16 bytes per access; a vector's right neighbour comes from the next
+// lane by shuffle.
+constexpr int kVecItems = 8;                              // 16-byte vectors per thread
+constexpr int kVecChunk = kConvThreads * 4 * kVecItems;   // dense elements per block
+
+// elements [i, i + 4) of a 4-byte dense buffer (i a multiple of 4; elements beyond n read 0)
+PSK_D uint4 load_vec4(const void* dense, long long i, long long n) {
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(dense);
+  if (i + 3 < n) return *reinterpret_cast<const uint4*>(p + i);
+  uint4 r = make_uint4(0, 0, 0, 0);
+  if (i < n) r.x = p[i];
+  if (i + 1 < n) r.y = p[i + 1];
+  if (i + 2 < n) r.z = p[i + 2];
+  return r;
+}
+
+// bit j set: element i + j exists and closes a run (last element, or differs from i + j + 1)
+template <int DT>
+PSK_D unsigned close_flags4(const void* dense, long long i, long long n, const uint4& v) {
+  // first element of the vector to the right: the next lane holds it, lane 31 loads it
+  uint32_t nx = __shfl_down_sync(0xffffffffu, v.x, 1);
+  if ((threadIdx.x & 31) == 31 && i + 4 < n) nx = reinterpret_cast<const uint32_t*>(dense)[i + 4];
+  unsigned f = 0;
+  if (i < n && (i == n - 1 || typed_differs<DT>(v.x, v.y))) f |= 1u;
+  if (i + 1 < n && (i + 1 == n - 1 || typed_differs<DT>(v.y, v.z))) f |= 2u;
+  if (i + 2 < n && (i + 2 == n - 1 || typed_differs<DT>(v.z, v.w))) f |= 4u;
+  if (i + 3 < n && (i + 3 == n - 1 || typed_differs<DT>(v.w, nx))) f |= 8u;
+  return f;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kConvThreads) k_encode_count_vec(const void* dense, long long n,
+                                                                   int32_t* block_count) {
+  __shared__ int32_t s_warp[kConvThreads / 32];
+  const long long base = (long long)blockIdx.x * kVecChunk;
+  int32_t c = 0;
+#pragma unroll
+  for (int it = 0; it < kVecItems; ++it) {
+    const long long i = base + ((long long)it * kConvThreads + threadIdx.x) * 4;
+    const uint4 v = load_vec4(dense, i, n);
+    c += __popc(close_flags4<DT>(dense, i, n, v));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t t = 0;
+    for (int w = 0; w < kConvThreads / 32; ++w) t += s_warp[w];
+    block_count[blockIdx.x] = t;
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kConvThreads) k_encode_write_vec(const void* dense, long long n,
+                                                                   const int32_t* block_off,
+                                                                   int32_t* ends, uint32_t* vals) {
+  constexpr int W = kConvThreads / 32;
+  __shared__ int32_t s_tot[kVecItems][W];  // runs closed by warp w in item it
+  const long long base = (long long)blockIdx.x * kVecChunk;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint4 v[kVecItems];
+  unsigned f[kVecItems];
+  int32_t before[kVecItems];  // runs closed by lower lanes of this warp in the same item
+#pragma unroll
+  for (int it = 0; it < kVecItems; ++it) {
+    const long long i = base + ((long long)it * kConvThreads + threadIdx.x) * 4;
+    v[it] = load_vec4(dense, i, n);
+    f[it] = close_flags4<DT>(dense, i, n, v[it]);
+    const int32_t c = __popc(f[it]);
+    int32_t inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    before[it] = inc - c;
+    if (lane == 31) s_tot[it][warp] = inc;
+  }
+  __syncthreads();
+  // output order = element order: items, then warps, then lanes, then the 4 elements
+  int32_t pos = block_off[blockIdx.x];
+#pragma unroll
+  for (int it = 0; it < kVecItems; ++it) {
+    int32_t mine = pos + before[it];
+    int32_t tot = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const int32_t c = s_tot[it][w];
+      if (w < warp) mine += c;
+      tot += c;
+    }
+    const long long i = base + ((long long)it * kConvThreads + threadIdx.x) * 4;
+    const uint32_t x[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (f[it] & (1u << j)) {
+        ends[mine] = (int32_t)(i + j + 1);
+        vals[mine] = x[j];
+        ++mine;
+      }
+    }
+    pos += tot;
+  }
+}
+
+// expand, 4 consecutive elements per thread and access: one search, then a linear advance;
+// the chunk's run values are staged next to its ends
+template <int DT>
+__global__ void __launch_bounds__(kConvThreads) k_expand_vec(const int32_t* ends, const uint32_t* vals,
+                                                             int32_t nruns, long long n, void* dense) {
+  __shared__ int32_t s_ends[kConvChunk + 1];
+  __shared__ uint32_t s_vals[kConvChunk + 1];
+  __shared__ int32_t s_r0, s_nr;
+  const long long b0 = (long long)blockIdx.x * kConvChunk;
+  long long b1 = b0 + kConvChunk;
+  if (b1 > n) b1 = n;
+  if (threadIdx.x < 2) {
+    int32_t pos = threadIdx.x == 0 ? (int32_t)b0 : (int32_t)(b1 - 1);
+    int32_t lo = 0, hi = nruns;
+    while (lo < hi) {
+      int32_t mid = lo + ((hi - lo) >> 1);
+      if (ends[mid] <= pos) lo = mid + 1; else hi = mid;
+    }
+    if (threadIdx.x == 0) s_r0 = lo; else s_nr = lo;
+  }
+  __syncthreads();
+  const int32_t r0 = s_r0;
+  const int32_t nr = s_nr - r0 + 1;
+  for (int32_t j = threadIdx.x; j < nr; j += kConvThreads) {
+    s_ends[j] = ends[r0 + j];
+    s_vals[j] = vals[r0 + j];
+  }
+  __syncthreads();
+  uint32_t* const out = reinterpret_cast<uint32_t*>(dense);
+  for (int it = 0; it < kConvItems / 4; ++it) {
+    const long long i = b0 + ((long long)it * kConvThreads + threadIdx.x) * 4;
+    if (i >= b1) continue;
+    int32_t lo = 0, hi = nr - 1;  // run of element i
+    while (lo < hi) {
+      int32_t mid = (lo + hi) >> 1;
+      if (s_ends[mid] <= (int32_t)i) lo = mid + 1; else hi = mid;
+    }
+    uint32_t x[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      while (lo < nr - 1 && s_ends[lo] <= (int32_t)(i + j)) ++lo;
+      x[j] = s_vals[lo];
+    }
+    if (i + 3 < b1) {
+      *reinterpret_cast<uint4*>(out + i) = make_uint4(x[0], x[1], x[2], x[3]);
+    } else {
+      for (int j = 0; j < 4 && i + j < b1; ++j) out[i + j] = x[j];
+    }
+  }
+}
+
 // expand: each block writes kConvChunk consecutive dense elements
 template <int DT>
 __global__ void __launch_bounds__(kConvThreads) k_expand(const int32_t* ends, const uint32_t* vals,

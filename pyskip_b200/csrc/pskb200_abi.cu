@@ -58,6 +58,7 @@ struct Ctx {
   unsigned long long phase_cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int64_t jit_min_runs = 1 << 18;  // evaluations at least this large get a specialised kernel
   int64_t jit_launches = 0;
+  bool convert_vec = false;        // dense <-> RLE with 16-byte accesses (psk_set_vector_conversion)
   int64_t small_partition = 2048;  // samples up to which one block does the whole partition
   int stagger_ns = 0;
   unsigned long long* trace_buf = nullptr;  // PSK_PHASE_TIMING builds: device trace buffer
@@ -342,11 +343,15 @@ psk_status finish_runs_store(psk_store_s* s, int64_t nruns) {
 namespace {
 template <int DT>
 psk_status encode_device(const void* d_dense, int64_t n, psk_store_t* out) {
-  const int32_t nb = (int32_t)((n + kConvChunk - 1) / kConvChunk);
+  // 16-byte accesses for 4-byte elements in an aligned buffer (psk_set_vector_conversion)
+  const bool vec = g.convert_vec && (DT == PSK_I32 || DT == PSK_F32) &&
+                   (reinterpret_cast<uintptr_t>(d_dense) & 15) == 0;
+  const int32_t nb = (int32_t)((n + (vec ? kVecChunk : kConvChunk) - 1) / (vec ? kVecChunk : kConvChunk));
   int32_t* d_counts = nullptr;
   psk_status st = dmalloc(reinterpret_cast<void**>(&d_counts), (size_t)(nb + 1) * 4);
   if (st != PSK_OK) return st;
-  LAUNCH(k_encode_count<DT>, nb, kConvThreads, 0, d_dense, (long long)n, d_counts);
+  if (vec) LAUNCH(k_encode_count_vec<DT>, nb, kConvThreads, 0, d_dense, (long long)n, d_counts);
+  else LAUNCH(k_encode_count<DT>, nb, kConvThreads, 0, d_dense, (long long)n, d_counts);
   LAUNCH(k_scan_counts, 1, 1024, 0, d_counts, nb, d_counts + nb);
   CUDA_TRY(cudaMemcpyAsync(g.h_ctrl, d_counts + nb, 4, cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
@@ -358,7 +363,8 @@ psk_status encode_device(const void* d_dense, int64_t n, psk_store_t* out) {
     cudaFreeAsync(d_counts, g.stream);
     return st;
   }
-  LAUNCH(k_encode_write<DT>, nb, kConvThreads, 0, d_dense, (long long)n, d_counts, s->d_ends, s->d_vals);
+  if (vec) LAUNCH(k_encode_write_vec<DT>, nb, kConvThreads, 0, d_dense, (long long)n, d_counts, s->d_ends, s->d_vals);
+  else LAUNCH(k_encode_write<DT>, nb, kConvThreads, 0, d_dense, (long long)n, d_counts, s->d_ends, s->d_vals);
   CUDA_TRY(cudaFreeAsync(d_counts, g.stream));
   s->nruns = nruns;
   s->span = (int32_t)n;
@@ -481,6 +487,12 @@ int64_t psk_launch_count(int32_t reset) {
 }
 
 int64_t psk_live_bytes(void) { return g.live_bytes.load(); }
+
+psk_status psk_set_vector_conversion(int32_t enable) {
+  std::lock_guard<std::recursive_mutex> api_lock_(g.api_mu);
+  g.convert_vec = enable != 0;
+  return PSK_OK;
+}
 
 psk_status psk_set_small_partition(int64_t max_samples) {
   std::lock_guard<std::recursive_mutex> api_lock_(g.api_mu);
@@ -712,6 +724,13 @@ psk_status psk_store_to_dense_device(psk_store_t s, void* d_out) {
   READY(s);
   const long long n = s->span;
   const unsigned nb = (unsigned)((n + kConvChunk - 1) / kConvChunk);
+  if (g.convert_vec && (s->dtype == PSK_I32 || s->dtype == PSK_F32) &&
+      (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {
+    // same block geometry, 16-byte stores (the two 4-byte types share the payload path)
+    LAUNCH(k_expand_vec<PSK_I32>, nb, kConvThreads, 0, s->d_ends, s->d_vals, (int32_t)s->nruns, n, d_out);
+    CUDA_TRY(cudaGetLastError());
+    return PSK_OK;
+  }
   switch (s->dtype) {
     case PSK_I32: LAUNCH(k_expand<PSK_I32>, nb, kConvThreads, 0, s->d_ends, s->d_vals, (int32_t)s->nruns, n, d_out); break;
     case PSK_F32: LAUNCH(k_expand<PSK_F32>, nb, kConvThreads, 0, s->d_ends, s->d_vals, (int32_t)s->nruns, n, d_out); break;

@@ -42,6 +42,10 @@ struct int2 {
   int x, y;
 };
 inline int2 make_int2(int x, int y) { return int2{x, y}; }
+struct alignas(16) uint4 {
+  unsigned x, y, z, w;
+};
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 
 struct psk_sim_uint3 {
   unsigned x = 0, y = 0, z = 0;

@@ -326,3 +326,37 @@ def test_jit_source_compiles_for_sm100a():
     if not ok and "libnvrtc not found" in log:
         pytest.skip("libnvrtc not installed")
     assert ok, log[:2000]
+
+
+def test_vector_conversion_kernels_match_scalar(lib):
+    """psk_set_vector_conversion: the 16-byte dense <-> RLE kernels give the same stores and the
+    same dense arrays as the scalar ones (and as numpy), for lengths around every vector,
+    warp, item and block boundary, for -0.0 / NaN floats, and for all-equal / all-different data."""
+    rng = np.random.default_rng(80)
+    cases = []
+    for n in (1, 2, 3, 4, 5, 31, 127, 128, 129, 1023, 1024, 1025, 4099, 8191, 8192, 8193, 20_000, 70_001):
+        dense = O.to_dense(*rand_runs(rng, n, max(1, n // int(rng.integers(1, 40)))))
+        cases.append(dense.astype(np.int32))
+    cases.append(np.arange(9000, dtype=np.int32))                       # every element its own run
+    cases.append(np.full(9000, 7, np.int32))                            # one run
+    f = (rng.integers(0, 3, 5003) * 0.5).astype(np.float32)
+    f[100:110] = -0.0
+    f[200:204] = np.nan
+    cases.append(f)
+    try:
+        for x in cases:
+            lib.set_vector_conversion(False)
+            s0 = lib.store_from_dense(x)
+            e0, v0 = s0.runs()
+            lib.set_vector_conversion(True)
+            s1 = lib.store_from_dense(x)
+            e1, v1 = s1.runs()
+            assert_runs_equal((e1, v1), (e0, v0), f"encode n={x.size}")
+            we, wv = O.to_store(x)
+            assert_runs_equal((e1, v1), (we, wv.astype(x.dtype)), f"encode vs oracle n={x.size}")
+            back = s1.to_dense()
+            assert back.dtype == x.dtype and np.array_equal(back.view(np.uint32), x.view(np.uint32)) or \
+                (x.dtype == np.float32 and np.array_equal(np.isnan(back), np.isnan(x))
+                 and np.array_equal(back[~np.isnan(x)], x[~np.isnan(x)]))
+    finally:
+        lib.set_vector_conversion(False)

@@ -18,6 +18,9 @@ from test_full_size import _terrain
 
 lib = A.lib()
 lib.init(0)
+if "--vec" in sys.argv:      # the 16-byte kernels (psk_set_vector_conversion); default: the scalar ones
+    lib.set_vector_conversion(True)
+    print("vector conversion kernels")
 peak = 6535.4
 try:
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", peak)
