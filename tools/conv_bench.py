@@ -67,7 +67,6 @@ if os.environ.get("PSK_CONV_CPROFILE") == "1":
         E.synchronize()
     pr.disable()
     pstats.Stats(pr).sort_stats("tottime").print_stats(14)
-    tm = lib.c.psk_timer_start
     sys.exit(0)
 dt = float(np.median(times))
 ms, nev, ri, ro = lib.profile_read()
