@@ -21,11 +21,13 @@
  *   - every entry point returns a psk_status; psk_last_error() gives the thread-local
  *     message.  PSK_EINVAL <-> std::invalid_argument (CHECK_ARGUMENT, detail/errors.hpp:7-13),
  *     PSK_ESTATE <-> std::logic_error (CHECK_STATE, errors.hpp:15-21).
- *   - stores are immutable, reference counted, and live in device memory (HBM) as two
- *     arrays: int32 ends[nruns] (strictly increasing exclusive run ends, ends[nruns-1] ==
- *     span) and uint32 vals[nruns] (32-bit payload: int32, float32 bits, bool 0/1, char
- *     sign-extended) -- the layout of core::Store (detail/core.hpp:12-62) with the Box
- *     (detail/box.hpp:11-127) flattened to its 4 information bytes.
+ *   - stores are immutable, reference counted, and live in device memory (HBM) as ONE array
+ *     of nruns 8-byte pairs { int32 end; uint32 payload }: ends are the strictly increasing
+ *     exclusive run ends (the last one == span), the payload is the 32-bit value (int32,
+ *     float32 bits, bool 0/1, char sign-extended) -- core::Store (detail/core.hpp:12-62)
+ *     interleaved, with the Box (detail/box.hpp:11-127) flattened to its 4 information
+ *     bytes, so that a tile of runs is one contiguous piece of memory for the copy engine.
+ *     The host-facing calls keep the reference's two-array form (ends[], vals[]).
  *   - all work is issued on one library stream per process; calls that return data to the
  *     host synchronise that stream, everything else is asynchronous.
  *   - there is NO CPU implementation behind this ABI.  Without a CUDA device every compute
@@ -182,6 +184,10 @@ PSK_API psk_status psk_set_vector_conversion(int32_t enable);
  * `prog` over k sources compiles to an sm_100a cubin; the compiler log goes to `log`. */
 PSK_API int32_t psk_jit_compile_check(int32_t k, int32_t nprog, const psk_node* prog, char* log,
                                       int32_t loglen);
+/* Tuning aid: tile geometry of the specialised kernels -- threads per CTA (multiple of 32) and
+ * runs per tile (multiple of 64).  The partition and the number of resident CTAs follow.
+ * Results do not depend on it.  Also read once from PSKB200_TILE_THREADS / PSKB200_TILE_CAP. */
+PSK_API psk_status psk_set_tile_geometry(int32_t threads, int32_t cap);
 /* How many psk_eval calls ran on a specialised kernel. */
 PSK_API int64_t psk_jit_launch_count(void);
 /* Measurement aid for bench.py's roofline line: when enabled, psk_eval brackets its
@@ -226,9 +232,9 @@ PSK_API psk_status psk_store_runs(psk_store_t s, int32_t* ends, void* vals);
 PSK_API int64_t psk_store_nruns(psk_store_t s);
 PSK_API int32_t psk_store_span(psk_store_t s);
 PSK_API int32_t psk_store_dtype(psk_store_t s);
-/* Device pointers of the run arrays (valid while the store is alive). */
-PSK_API psk_status psk_store_device_ptrs(psk_store_t s, const int32_t** d_ends,
-                                         const uint32_t** d_vals);
+/* Device pointer of the run array (valid while the store is alive): nruns pairs of
+ * { int32 end; uint32 payload }, followed by two sentinel pairs (end = INT32_MAX). */
+PSK_API psk_status psk_store_device_pairs(psk_store_t s, const void** d_pairs);
 /* The payload of run 0 (used for 1-run stores, i.e. scalars). */
 PSK_API psk_status psk_store_first_value(psk_store_t s, uint32_t* bits);
 PSK_API void psk_store_retain(psk_store_t s);

@@ -104,10 +104,10 @@ def make_view(kind, shape, comps=None, scale=None, offset=None) -> View:
 _SYMBOLS = [
     "psk_last_error", "psk_version", "psk_is_simulator", "psk_init", "psk_device_count",
     "psk_synchronize", "psk_get_stream", "psk_set_stream", "psk_timer_start", "psk_timer_stop", "psk_launch_count",
-    "psk_live_bytes", "psk_profile", "psk_profile_read", "psk_set_jit_threshold", "psk_set_small_partition", "psk_set_vector_conversion", "psk_jit_launch_count", "psk_jit_compile_check", "psk_store_from_runs", "psk_store_from_runs_async", "psk_store_runs_async", "psk_copy_synchronize", "psk_store_from_device_runs", "psk_store_fill",
+    "psk_live_bytes", "psk_profile", "psk_profile_read", "psk_set_jit_threshold", "psk_set_tile_geometry", "psk_set_small_partition", "psk_set_vector_conversion", "psk_jit_launch_count", "psk_jit_compile_check", "psk_store_from_runs", "psk_store_from_runs_async", "psk_store_runs_async", "psk_copy_synchronize", "psk_store_from_device_runs", "psk_store_fill",
     "psk_store_from_dense", "psk_store_from_dense_device", "psk_store_to_dense",
     "psk_store_to_dense_device", "psk_store_runs", "psk_store_nruns", "psk_store_span",
-    "psk_store_dtype", "psk_store_device_ptrs", "psk_store_first_value", "psk_eval_async", "psk_store_retain",
+    "psk_store_dtype", "psk_store_device_pairs", "psk_store_first_value", "psk_eval_async", "psk_store_retain",
     "psk_store_release", "psk_eval", "psk_view_span", "psk_mask_nd", "psk_reduce",
     "psk_store_boundary", "psk_store_boundary_device", "psk_store_slice",
 ]
@@ -158,10 +158,11 @@ class Store:
         self.lib._chk(self.lib.c.psk_store_to_dense(C.c_void_p(self.h), out.ctypes.data_as(C.c_void_p)))
         return out
 
-    def device_ptrs(self):
-        e, v = C.c_void_p(), C.c_void_p()
-        self.lib._chk(self.lib.c.psk_store_device_ptrs(C.c_void_p(self.h), C.byref(e), C.byref(v)))
-        return e.value, v.value
+    def device_pairs(self):
+        """Device address of the store's (end, payload) int32 pairs."""
+        ptr = C.c_void_p()
+        self.lib._chk(self.lib.c.psk_store_device_pairs(C.c_void_p(self.h), C.byref(ptr)))
+        return ptr.value
 
 
 class Lib:
@@ -202,7 +203,7 @@ class Lib:
         c.psk_store_to_dense.argtypes = [C.c_void_p, C.c_void_p]
         c.psk_store_to_dense_device.argtypes = [C.c_void_p, C.c_void_p]
         c.psk_store_runs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-        c.psk_store_device_ptrs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        c.psk_store_device_pairs.argtypes = [C.c_void_p, C.c_void_p]
         c.psk_store_first_value.argtypes = [C.c_void_p, C.c_void_p]
         c.psk_store_boundary_device.argtypes = [C.c_void_p, C.c_void_p]
         c.psk_store_boundary.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -258,6 +259,9 @@ class Lib:
 
     def set_jit_threshold(self, min_total_runs: int):
         self._chk(self.c.psk_set_jit_threshold(C.c_int64(min_total_runs)))
+
+    def set_tile_geometry(self, threads: int, cap: int):
+        self._chk(self.c.psk_set_tile_geometry(C.c_int32(threads), C.c_int32(cap)))
 
     def set_vector_conversion(self, enable: bool):
         self._chk(self.c.psk_set_vector_conversion(1 if enable else 0))

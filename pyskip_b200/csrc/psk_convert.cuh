@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(1024) k_scan_counts(int32_t* counts, int32_t n
 template <int DT>
 __global__ void __launch_bounds__(kConvThreads) k_encode_write(const void* dense, long long n,
                                                                const int32_t* block_off,
-                                                               int32_t* ends, uint32_t* vals) {
+                                                               int2* runs) {
   __shared__ int32_t s_warp[kConvThreads / 32 + 1];
   const long long base = (long long)blockIdx.x * kConvChunk;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -130,10 +130,7 @@ __global__ void __launch_bounds__(kConvThreads) k_encode_write(const void* dense
       if (w < warp) woff += cw;
       tot += cw;
     }
-    if (b) {
-      ends[running + woff + wpos] = (int32_t)(i + 1);
-      vals[running + woff + wpos] = v;
-    }
+    if (b) runs[running + woff + wpos] = make_int2((int32_t)(i + 1), (int32_t)v);
     running += tot;
     __syncthreads();
   }
@@ -199,7 +196,7 @@ __global__ void __launch_bounds__(kConvThreads) k_encode_count_vec(const void* d
 template <int DT>
 __global__ void __launch_bounds__(kConvThreads) k_encode_write_vec(const void* dense, long long n,
                                                                    const int32_t* block_off,
-                                                                   int32_t* ends, uint32_t* vals) {
+                                                                   int2* runs) {
   constexpr int W = kConvThreads / 32;
   __shared__ int32_t s_tot[kVecItems][W];  // runs closed by warp w in item it
   const long long base = (long long)blockIdx.x * kVecChunk;
@@ -240,8 +237,7 @@ __global__ void __launch_bounds__(kConvThreads) k_encode_write_vec(const void* d
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (f[it] & (1u << j)) {
-        ends[mine] = (int32_t)(i + j + 1);
-        vals[mine] = x[j];
+        runs[mine] = make_int2((int32_t)(i + j + 1), (int32_t)x[j]);
         ++mine;
       }
     }
@@ -252,7 +248,7 @@ __global__ void __launch_bounds__(kConvThreads) k_encode_write_vec(const void* d
 // expand, 4 consecutive elements per thread and access: one search, then a linear advance;
 // the chunk's run values are staged next to its ends
 template <int DT>
-__global__ void __launch_bounds__(kConvThreads) k_expand_vec(const int32_t* ends, const uint32_t* vals,
+__global__ void __launch_bounds__(kConvThreads) k_expand_vec(const int2* runs,
                                                              int32_t nruns, long long n, void* dense) {
   __shared__ int32_t s_ends[kConvChunk + 1];
   __shared__ uint32_t s_vals[kConvChunk + 1];
@@ -265,7 +261,7 @@ __global__ void __launch_bounds__(kConvThreads) k_expand_vec(const int32_t* ends
     int32_t lo = 0, hi = nruns;
     while (lo < hi) {
       int32_t mid = lo + ((hi - lo) >> 1);
-      if (ends[mid] <= pos) lo = mid + 1; else hi = mid;
+      if (runs[mid].x <= pos) lo = mid + 1; else hi = mid;
     }
     if (threadIdx.x == 0) s_r0 = lo; else s_nr = lo;
   }
@@ -273,8 +269,9 @@ __global__ void __launch_bounds__(kConvThreads) k_expand_vec(const int32_t* ends
   const int32_t r0 = s_r0;
   const int32_t nr = s_nr - r0 + 1;
   for (int32_t j = threadIdx.x; j < nr; j += kConvThreads) {
-    s_ends[j] = ends[r0 + j];
-    s_vals[j] = vals[r0 + j];
+    const int2 r = runs[r0 + j];
+    s_ends[j] = r.x;
+    s_vals[j] = (uint32_t)r.y;
   }
   __syncthreads();
   uint32_t* const out = reinterpret_cast<uint32_t*>(dense);
@@ -302,7 +299,7 @@ __global__ void __launch_bounds__(kConvThreads) k_expand_vec(const int32_t* ends
 
 // expand: each block writes kConvChunk consecutive dense elements
 template <int DT>
-__global__ void __launch_bounds__(kConvThreads) k_expand(const int32_t* ends, const uint32_t* vals,
+__global__ void __launch_bounds__(kConvThreads) k_expand(const int2* runs,
                                                          int32_t nruns, long long n, void* dense) {
   __shared__ int32_t s_ends[kConvChunk + 1];
   __shared__ int32_t s_r0, s_nr;
@@ -315,14 +312,14 @@ __global__ void __launch_bounds__(kConvThreads) k_expand(const int32_t* ends, co
     int32_t lo = 0, hi = nruns;
     while (lo < hi) {
       int32_t mid = lo + ((hi - lo) >> 1);
-      if (ends[mid] <= pos) lo = mid + 1; else hi = mid;
+      if (runs[mid].x <= pos) lo = mid + 1; else hi = mid;
     }
     if (threadIdx.x == 0) s_r0 = lo; else s_nr = lo;
   }
   __syncthreads();
   const int32_t r0 = s_r0;
   const int32_t nr = s_nr - r0 + 1;  // <= elements in the chunk
-  for (int32_t j = threadIdx.x; j < nr; j += kConvThreads) s_ends[j] = ends[r0 + j];
+  for (int32_t j = threadIdx.x; j < nr; j += kConvThreads) s_ends[j] = runs[r0 + j].x;
   __syncthreads();
   for (int it = 0; it < kConvItems; ++it) {
     long long i = b0 + it * kConvThreads + threadIdx.x;
@@ -332,7 +329,7 @@ __global__ void __launch_bounds__(kConvThreads) k_expand(const int32_t* ends, co
         int32_t mid = (lo + hi) >> 1;
         if (s_ends[mid] <= (int32_t)i) lo = mid + 1; else hi = mid;
       }
-      store_payload<DT>(dense, i, vals[r0 + lo]);
+      store_payload<DT>(dense, i, (uint32_t)runs[r0 + lo].y);
     }
   }
 }
@@ -350,18 +347,17 @@ PSK_HD uint32_t sel_pos(const DView& v, uint32_t j) {
 
 // raw run list of a box mask: per segment (a dim-0 row when stride_0 == 1, else one
 // element) an excluded run ending at its start and an included run ending at its end
-__global__ void k_mask_segments(DView v, uint32_t seg_len, int32_t nseg, int32_t* ends, uint32_t* vals) {
+__global__ void k_mask_segments(DView v, uint32_t seg_len, int32_t nseg, int2* runs) {
   int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < nseg) {
     uint32_t start = sel_pos(v, (uint32_t)s * seg_len);
-    ends[2 * s] = (int32_t)start;
-    vals[2 * s] = 0;
-    ends[2 * s + 1] = (int32_t)(start + seg_len);
-    vals[2 * s + 1] = 1;
+    runs[2 * s] = make_int2((int32_t)start, 0);
+    runs[2 * s + 1] = make_int2((int32_t)(start + seg_len), 1);
   }
   if (s == 0) {
-    ends[2 * nseg] = (int32_t)v.n;
-    vals[2 * nseg] = 0;
+    runs[2 * nseg] = make_int2((int32_t)v.n, 0);
+    runs[2 * nseg + 1] = make_int2(0x7fffffff, 0);  // sentinel pairs behind the last run
+    runs[2 * nseg + 2] = make_int2(0x7fffffff, 0);
   }
 }
 
@@ -402,14 +398,16 @@ PSK_D void red_merge(RedAcc& a, const RedAcc& b, int op) {
 }
 
 template <bool IS_F>
-__global__ void __launch_bounds__(kRedThreads) k_reduce_partial(const int32_t* ends, const uint32_t* vals,
-                                                                int32_t nruns, int op, RedAcc* partial) {
+__global__ void __launch_bounds__(kRedThreads) k_reduce_partial(const int2* runs, int32_t nruns,
+                                                                const int32_t* d_count, int op, RedAcc* partial) {
   __shared__ RedAcc s_acc[kRedThreads];
   RedAcc acc;
   acc.any = 0; acc.isum = 0; acc.fsum = 0; acc.mx = 0; acc.mn = 0;
+  if (d_count) nruns = *d_count;  // a queued result: its run count is still on the device
   for (int32_t i = blockIdx.x * kRedThreads + threadIdx.x; i < nruns; i += gridDim.x * kRedThreads) {
-    uint32_t len = (uint32_t)(ends[i] - (i ? ends[i - 1] : 0));
-    uint32_t v = vals[i];
+    const int2 r_ = runs[i];
+    uint32_t len = (uint32_t)(r_.x - (i ? runs[i - 1].x : 0));
+    uint32_t v = (uint32_t)r_.y;
     RedAcc r;
     r.any = 1; r.mx = v; r.mn = v;
     if (op == PSK_RED_PROD) {

@@ -189,9 +189,10 @@ std::string gen_source(int K, bool typed_float, bool views, int nprog, const psk
   return src;
 }
 
-std::string cache_key(int K, bool typed_float, bool views, int nprog, const psk_node* prog) {
+std::string cache_key(int K, bool typed_float, bool views, int T, int CAP, int nprog, const psk_node* prog) {
   std::string key;
-  key.reserve(nprog * 3 + 8);
+  key.reserve(nprog * 3 + 24);
+  key += std::to_string(T) + "/" + std::to_string(CAP) + "/";
   key += (char)K;
   key += typed_float ? 'T' : 'B';
   key += views ? 'V' : 'F';
@@ -202,8 +203,8 @@ std::string cache_key(int K, bool typed_float, bool views, int nprog, const psk_
   return key;
 }
 
-bool compile_cubin(int K, bool typed_float, bool views, int nprog, const psk_node* prog, std::vector<char>* cubin,
-                   std::string* why) {
+bool compile_cubin(int K, bool typed_float, bool views, int T, int CAP, int nprog, const psk_node* prog,
+                   std::vector<char>* cubin, std::string* why) {
   const std::string src = gen_source(K, typed_float, views, nprog, prog);
   nvrtcProgram np = nullptr;
   int r = g_api.nvrtcCreateProgram(&np, src.c_str(), "psk_jit_merge_eval.cu", kJitNumHeaders, kJitHeaderSources,
@@ -212,19 +213,13 @@ bool compile_cubin(int K, bool typed_float, bool views, int nprog, const psk_nod
     *why = std::string("nvrtcCreateProgram: ") + g_api.nvrtcGetErrorString(r);
     return false;
   }
+  const std::string opt_t = "-DPSK_TILE_THREADS=" + std::to_string(T);
+  const std::string opt_c = "-DPSK_TILE_CAP=" + std::to_string(CAP);
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo",
 #ifdef PSK_PHASE_TIMING
                         "-DPSK_PHASE_TIMING",
 #endif
-#ifdef PSK_TILE_THREADS
-                        "-DPSK_TILE_THREADS=" PSK_STR(PSK_TILE_THREADS),
-#endif
-#ifdef PSK_TILE_CAP
-                        "-DPSK_TILE_CAP=" PSK_STR(PSK_TILE_CAP),
-#endif
-#ifdef PSK_COARSE_SEARCH
-                        "-DPSK_COARSE_SEARCH=" PSK_STR(PSK_COARSE_SEARCH),
-#endif
+                        opt_t.c_str(), opt_c.c_str(),
   };
   r = g_api.nvrtcCompileProgram(np, (int)(sizeof(opts) / sizeof(opts[0])), opts);
   if (r != 0) {
@@ -256,9 +251,10 @@ bool compile_cubin(int K, bool typed_float, bool views, int nprog, const psk_nod
   return true;
 }
 
-JitKernel* compile(int K, bool typed_float, bool views, int nprog, const psk_node* prog, std::string* why) {
+JitKernel* compile(int K, bool typed_float, bool views, int T, int CAP, int nprog, const psk_node* prog,
+                   std::string* why) {
   std::vector<char> cubin;
-  if (!compile_cubin(K, typed_float, views, nprog, prog, &cubin, why)) return nullptr;
+  if (!compile_cubin(K, typed_float, views, T, CAP, nprog, prog, &cubin, why)) return nullptr;
   void* mod = nullptr;
   int r = g_api.cuModuleLoadData(&mod, cubin.data());
   if (r != 0) {
@@ -278,20 +274,21 @@ JitKernel* compile(int K, bool typed_float, bool views, int nprog, const psk_nod
 
 }  // namespace
 
-const JitKernel* jit_get_merge_eval(int K, bool typed_float, bool views, int nprog, const psk_node* prog, const char** why) {
+const JitKernel* jit_get_merge_eval(int K, bool typed_float, bool views, int T, int CAP, int nprog,
+                                    const psk_node* prog, const char** why) {
   std::lock_guard<std::mutex> l(g_mu);
   static std::string s_why;
   if (!load_api()) {
     if (why) *why = g_api.why.c_str();
     return nullptr;
   }
-  const std::string key = cache_key(K, typed_float, views, nprog, prog);
+  const std::string key = cache_key(K, typed_float, views, T, CAP, nprog, prog);
   auto it = g_cache.find(key);
   if (it != g_cache.end()) {
     if (!it->second && why) *why = "previous compilation of this program failed";
     return it->second;
   }
-  JitKernel* k = compile(K, typed_float, views, nprog, prog, &s_why);
+  JitKernel* k = compile(K, typed_float, views, T, CAP, nprog, prog, &s_why);
   if (k) {
     ++g_compiled;
   } else {
@@ -318,12 +315,12 @@ int jit_launch(const JitKernel* k, unsigned grid, unsigned block, size_t smem, v
   return g_api.cuLaunchKernel(k->function, grid, 1, 1, block, 1, 1, (unsigned)smem, stream, args, nullptr);
 }
 
-int jit_compile_check(int K, bool typed_float, int nprog, const psk_node* prog, char* log, int loglen) {
+int jit_compile_check(int K, bool typed_float, int T, int CAP, int nprog, const psk_node* prog, char* log, int loglen) {
   std::lock_guard<std::mutex> l(g_mu);
   std::string why;
   std::vector<char> cubin;
-  bool ok = load_nvrtc() && compile_cubin(K, typed_float, false, nprog, prog, &cubin, &why) &&
-            compile_cubin(K, typed_float, true, nprog, prog, &cubin, &why);  // both staging variants
+  bool ok = load_nvrtc() && compile_cubin(K, typed_float, false, T, CAP, nprog, prog, &cubin, &why) &&
+            compile_cubin(K, typed_float, true, T, CAP, nprog, prog, &cubin, &why);  // both staging variants
   if (!ok && why.empty()) why = g_api.why;
   if (log && loglen > 0) {
     std::string msg = ok ? ("ok cubin bytes=" + std::to_string(cubin.size())) : why;

@@ -29,8 +29,13 @@ struct DView {
 };
 
 struct DSource {
-  const int32_t* ends;
-  const uint32_t* vals;
+  // (end, payload) pairs, 8 bytes per run, ends strictly increasing; pairs [nruns] and
+  // [nruns + 1] are sentinels (end = INT_MAX) and the allocation extends 4 pairs beyond nruns,
+  // so tile loads may run past the last run without a bounds test
+  const int2* runs;
+  // run count of a source that is itself a queued (deferred) result: read on the device by
+  // k_prepare; nruns then holds the capacity (an upper bound)
+  const int32_t* d_count;
   int32_t nruns;
   int32_t nviews;
   int32_t a, e;      // raw run-index range [a, e) that can contribute to the output
@@ -51,22 +56,18 @@ struct DPlan {
   int32_t max_tiles;
   int32_t out_capacity;
   int32_t any_views;
-  int32_t stagger_ns;  // start delay per CTA index: de-phases the persistent CTAs
+  int32_t on_device;  // 1: sample / tile counts are computed by k_prepare (views, deferred sources)
+  uint32_t epoch;     // tags the look-back words of this evaluation (the state buffer is reused)
   // scratch + output (device pointers)
-  int32_t* samp_keys;              // [max_samples] sample keys, source by source
-  int32_t* merged;                 // [max_samples] sorted sample keys
-  int32_t* bounds;                 // [(max_tiles+1) * k] per-tile raw index bounds
+  int32_t* bounds;                 // [(max_tiles+1) * k] per-tile raw index bounds (total order)
+  int2* lookahead;                 // [max_tiles * k] with views: first (mapped) run beyond the tile's hi
   int32_t* tile_hi;                // [max_tiles] inclusive upper coordinate of each tile
   unsigned long long* tile_state;  // [max_tiles] look-back chain
   int32_t* ctrl;                   // [0]=ticket [1]=out_count [2]=error
   unsigned long long* phase;       // [8] cycle counters (PSK_PHASE_TIMING builds only)
   unsigned long long* trace;       // [max_tiles * 8] per-tile globaltimer stamps (same builds)
-  int32_t* out_ends;
-  uint32_t* out_vals;
-  // single-tile evaluations (everything fits one tile, no views): the host writes the tile's
-  // bounds here and points `bounds` / `tile_hi` at them -- no partition kernels are launched
-  int32_t one_bounds[2 * PSK_MAX_SOURCES];
-  int32_t one_hi;
+  int2* out;                       // result pairs [out_capacity + 4]
+  int32_t* out_count;              // the result's run count, left on the device for consumers
   psk_node prog[PSK_MAX_PROGRAM];
   DSource src[PSK_MAX_SOURCES];
 };
@@ -138,7 +139,7 @@ PSK_HD int32_t map_chain(const DView* v, int nviews, int32_t E) {
 }
 
 PSK_HD int32_t mapped_end(const DSource& s, int32_t idx) {
-  int32_t E = s.ends[idx];
+  int32_t E = s.runs[idx].x;
   return s.nviews ? map_chain(s.v, s.nviews, E) : E;
 }
 

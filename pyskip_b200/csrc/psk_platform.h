@@ -50,6 +50,14 @@ PSK_D uint32_t ld_nc(const uint32_t* p) {
 #endif
 }
 
+PSK_D int2 ld_nc(const int2* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
 // predicated read-only load: *p if take, else dflt -- one @p LDG, never a branch
 PSK_D int32_t ld_nc_if(const int32_t* p, bool take, int32_t dflt) {
 #if defined(__CUDA_ARCH__)
@@ -67,7 +75,7 @@ PSK_D int32_t ld_nc_if(const int32_t* p, bool take, int32_t dflt) {
 // explicit ld.shared / st.shared: nvcc otherwise re-derives the generic address of dynamic
 // shared memory (S2R SR_CgaCtaId + LEA) inside the merge loop.
 struct SmemPairs {
-#if defined(__CUDA_ARCH__)
+#ifndef PSK_CPU_SIM
   uint32_t base;
   PSK_D explicit SmemPairs(void* p) {
     // volatile: computed once and kept in a register (never rematerialised in the loops)
@@ -89,6 +97,15 @@ struct SmemPairs {
   // A cursor is the shared-window byte address of a pair: loops that walk the buffer keep
   // cursors in registers and never recompute base + 8 * index.
   PSK_D uint32_t at(int i) const { return base + (uint32_t)i * 8u; }
+  PSK_D uint32_t dst(int i) const { return base + (uint32_t)i * 8u; }  // bulk-copy destination
+  PSK_D int ldy(int i) const {
+    int r;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(base + (uint32_t)i * 8u + 4u));
+    return r;
+  }
+  PSK_D void stx(int i, int x) const {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (uint32_t)i * 8u), "r"(x) : "memory");
+  }
   static PSK_D uint32_t step() { return 8u; }
   PSK_D void st_at(uint32_t c, int x, int y) const {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(c), "r"(x), "r"(y) : "memory");
@@ -106,6 +123,9 @@ struct SmemPairs {
   int2* ptr;
   explicit SmemPairs(void* p) : ptr(reinterpret_cast<int2*>(p)) {}
   uint32_t at(int i) const { return (uint32_t)i; }
+  unsigned char* dst(int i) const { return reinterpret_cast<unsigned char*>(ptr + i); }
+  int ldy(int i) const { return ptr[i].y; }
+  void stx(int i, int x) const { ptr[i].x = x; }
   static uint32_t step() { return 1u; }
   void st_at(uint32_t c, int x, int y) const { ptr[c] = make_int2(x, y); }
   void advance_if(int e, uint32_t& c, int& head, uint32_t& val) const {
@@ -120,6 +140,66 @@ struct SmemPairs {
   void st(int i, int x, int y) const { ptr[i] = make_int2(x, y); }
 #endif
 };
+
+
+// ---- mbarrier + bulk asynchronous copy (cp.async.bulk, the 1-D TMA form) ------------------
+// One thread arms the barrier with the byte count of the copies it issues; the copy engine
+// completes the phase when the bytes have landed in shared memory; every consumer thread
+// waits on the phase parity.  Source, destination and size must be multiples of 16 bytes.
+// (Simulator: the copy is a memcpy by the issuing thread; the barrier is a phase counter.)
+#ifndef PSK_CPU_SIM
+typedef unsigned long long psk_mbar_t;
+PSK_D uint32_t smem_addr(const void* p) {
+  uint32_t a;
+  asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(a) : "l"(p));
+  return a;
+}
+PSK_D void mbar_init(psk_mbar_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+PSK_D void mbar_arrive_expect_tx(psk_mbar_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+               : "memory");
+}
+PSK_D void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, psk_mbar_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(smem_addr(bar))
+      : "memory");
+}
+PSK_D void mbar_wait(psk_mbar_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n .reg .pred q;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n"
+      " @q bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+#else
+struct psk_mbar_t {
+  volatile long long pending;
+  volatile unsigned phases;  // completed phases
+};
+inline void mbar_init(psk_mbar_t* bar, int) {
+  bar->pending = 0;
+  bar->phases = 0;
+}
+inline void mbar_arrive_expect_tx(psk_mbar_t* bar, uint32_t bytes) {
+  if (bytes == 0) {
+    __atomic_fetch_add(&bar->phases, 1u, __ATOMIC_SEQ_CST);
+  } else {
+    __atomic_store_n(&bar->pending, (long long)bytes, __ATOMIC_SEQ_CST);
+  }
+}
+inline void bulk_g2s(unsigned char* dst_smem, const void* src, uint32_t bytes, psk_mbar_t* bar) {
+  memcpy(dst_smem, src, bytes);
+  if (__atomic_sub_fetch(&bar->pending, (long long)bytes, __ATOMIC_SEQ_CST) == 0)
+    __atomic_fetch_add(&bar->phases, 1u, __ATOMIC_SEQ_CST);
+}
+inline void mbar_wait(psk_mbar_t* bar, uint32_t parity) {
+  while ((__atomic_load_n(&bar->phases, __ATOMIC_SEQ_CST) & 1u) == parity) std::this_thread::yield();
+}
+#endif
 
 PSK_D void sleep_ns(unsigned ns) {
 #if defined(__CUDA_ARCH__)

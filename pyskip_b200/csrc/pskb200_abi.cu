@@ -30,9 +30,9 @@ struct psk_store_s {
   int64_t nruns = 0;
   int64_t capacity = 0;
   int32_t span = 0;
-  int32_t* d_ends = nullptr;
-  uint32_t* d_vals = nullptr;
-  cudaEvent_t ready = nullptr;  // async upload finished (waited on by the first consumer)
+  int2* d_runs = nullptr;       // (end, payload) pairs: capacity + kStorePad pairs; [nruns], [nruns+1] sentinels
+  int32_t* d_count = nullptr;   // the run count on the device (inside the padding of d_runs)
+  cudaEvent_t ready = nullptr;  // produced on another stream (async upload): consumers wait for it
   cudaEvent_t busy = nullptr;   // async download finished (waited on before the memory is freed)
   int32_t pending_slot = -1;    // result of psk_eval_async whose run count has not been read yet
   int32_t failed = 0;           // status of a psk_eval_async that turned out to have failed
@@ -61,6 +61,8 @@ struct Ctx {
   bool convert_vec = false;        // dense <-> RLE with 16-byte accesses (psk_set_vector_conversion)
   int64_t small_partition = 2048;  // samples up to which one block does the whole partition
   int stagger_ns = 0;
+  int jit_T = kTileThreads, jit_CAP = kTileCap;  // tile geometry of the specialised kernels (PSKB200_TILE_*)
+  cudaEvent_t xev = nullptr;                     // orders the download stream behind the library stream
   unsigned long long* trace_buf = nullptr;  // PSK_PHASE_TIMING builds: device trace buffer
   int64_t trace_cap = 0, trace_tiles = 0;
   // psk_eval_async: a ring of in-flight evaluations, each with its own pinned plan staging,
@@ -162,7 +164,14 @@ psk_status do_init(int device) {
   CUDA_TRY(cudaFuncSetAttribute(k_merge_eval_interp<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CUDA_TRY(cudaFuncSetAttribute(k_merge_eval_interp<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CUDA_TRY(cudaFuncSetAttribute(k_merge_eval_interp<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  if (const char* sv = getenv("PSKB200_STAGGER_NS")) g.stagger_ns = atoi(sv);
+  if (const char* sv = getenv("PSKB200_TILE_THREADS")) {  // tuning aid: geometry of the NVRTC kernels
+    const int t = atoi(sv);
+    if (t >= 32 && t <= 1024 && t % 32 == 0) g.jit_T = t;
+  }
+  if (const char* sv = getenv("PSKB200_TILE_CAP")) {
+    const int c = atoi(sv);
+    if (c >= 512 && c <= 13000 && c % 64 == 0) g.jit_CAP = c;
+  }
   g.device = device;
   g.inited = true;
   return PSK_OK;
@@ -188,22 +197,29 @@ psk_status dmalloc(void** p, size_t bytes) {
 
 int elem_size(int dtype) { return (dtype == PSK_I32 || dtype == PSK_F32) ? 4 : 1; }
 
+constexpr int64_t kStorePad = 4;  // pairs behind the capacity: 2 sentinels, tile-load slack, the count word
+
 psk_status new_store(int dtype, int64_t capacity, psk_store_t* out) {
   psk_store_s* s = new (std::nothrow) psk_store_s();
   if (!s) return fail(PSK_ENOMEM, "out of host memory");
   s->dtype = dtype;
   s->capacity = capacity;
-  // one spare word behind the ends: k_merge_eval leaves the run count there
-  psk_status st = dmalloc(reinterpret_cast<void**>(&s->d_ends), (size_t)(capacity + 1) * 4);
-  if (st == PSK_OK) st = dmalloc(reinterpret_cast<void**>(&s->d_vals), (size_t)capacity * 4);
+  psk_status st = dmalloc(reinterpret_cast<void**>(&s->d_runs), (size_t)(capacity + kStorePad) * 8);
   if (st != PSK_OK) {
-    if (s->d_ends) cudaFreeAsync(s->d_ends, g.stream);
     delete s;
     return st;
   }
+  // the last padding pair holds the run count for device-side consumers (queued results)
+  s->d_count = reinterpret_cast<int32_t*>(s->d_runs + capacity + kStorePad - 1);
   g.live_bytes += capacity * 8;
   *out = s;
   return PSK_OK;
+}
+
+// a store produced on a copy stream: make the library stream wait for it (idempotent; the
+// event lives until the store is released)
+void wait_ready(psk_store_s* s) {
+  if (s->ready) cudaStreamWaitEvent(g.stream, s->ready, 0);
 }
 
 // ---- view descriptors ----------------------------------------------------------------
@@ -286,51 +302,86 @@ psk_status validate_program(int k, int nprog, const psk_node* prog) {
 }  // namespace
 
 namespace {
-// checks 0 < ends[0] < ends[1] < ... on device; flag[0] |= 1 when violated
-__global__ void k_validate_runs(const int32_t* ends, int32_t n, int32_t* flag) {
-  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// host / device SoA run arrays -> the store's pair layout; checks 0 < ends[0] < ends[1] < ...
+// (flag[0] |= 1 when violated), widens 1-byte payloads, appends the sentinel pairs and the count
+template <int ELEM>  // payload bytes: 4, 1 (char, sign-extended), -1 (bool)
+__global__ void k_interleave(const int32_t* ends, const void* vals, int32_t n, int2* runs, int32_t* d_count,
+                             int32_t* flag) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    int32_t prev = i ? ends[i - 1] : 0;
-    if (ends[i] <= prev) atomicOr(flag, 1);
+    const int32_t e = ends[i];
+    const int32_t prev = i ? ends[i - 1] : 0;
+    if (e <= prev) atomicOr(flag, 1);
+    uint32_t v;
+    if (ELEM == 4) v = reinterpret_cast<const uint32_t*>(vals)[i];
+    else if (ELEM == 1) v = (uint32_t)(int32_t) reinterpret_cast<const int8_t*>(vals)[i];
+    else v = reinterpret_cast<const uint8_t*>(vals)[i] ? 1u : 0u;
+    runs[i] = make_int2(e, (int32_t)v);
+  }
+  if (i == 0) {
+    runs[n] = make_int2(kSentinel, 0);
+    runs[n + 1] = make_int2(kSentinel, 0);
+    *d_count = n;
+  }
+}
+
+// the store's pairs -> SoA arrays (Array.runs(), type_binds.hpp:145-151)
+template <int ELEM>
+__global__ void k_deinterleave(const int2* runs, int32_t n, int32_t* ends, void* vals) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int2 r = runs[i];
+    ends[i] = r.x;
+    if (ELEM == 4) reinterpret_cast<uint32_t*>(vals)[i] = (uint32_t)r.y;
+    else reinterpret_cast<uint8_t*>(vals)[i] = (uint8_t)r.y;
+  }
+}
+
+// sentinel pairs + device-side count behind runs that a kernel wrote (encode, concat, ...)
+__global__ void k_seal(int2* runs, int32_t n, int32_t* d_count) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    runs[n] = make_int2(kSentinel, 0);
+    runs[n + 1] = make_int2(kSentinel, 0);
+    *d_count = n;
   }
 }
 
 // (first payload, last payload, run count) of a store, as int64, for the stitch all-gather
-__global__ void k_boundary(const uint32_t* vals, int64_t nruns, const int32_t* d_count, long long* out3) {
+__global__ void k_boundary(const int2* runs, int64_t nruns, const int32_t* d_count, long long* out3) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     if (d_count) nruns = *d_count;  // result of psk_eval_async: the count is still on the device
-    out3[0] = (long long)vals[0];
-    out3[1] = (long long)vals[nruns - 1];
+    out3[0] = (long long)(uint32_t)runs[0].y;
+    out3[1] = (long long)(uint32_t)runs[nruns - 1].y;
     out3[2] = (long long)nruns;
   }
 }
 
-__global__ void k_fill_one(int32_t* ends, uint32_t* vals, int32_t span, uint32_t bits) {
+__global__ void k_fill_one(int2* runs, int32_t* d_count, int32_t span, uint32_t bits) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    ends[0] = span;
-    vals[0] = bits;
+    runs[0] = make_int2(span, (int32_t)bits);
+    runs[1] = make_int2(kSentinel, 0);
+    runs[2] = make_int2(kSentinel, 0);
+    *d_count = 1;
   }
 }
 
-// widen 1-byte host values (bool / char) to payloads
-__global__ void k_widen(const uint8_t* in, int32_t n, int is_bool, uint32_t* out) {
-  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = is_bool ? (in[i] ? 1u : 0u) : (uint32_t)(int32_t)(int8_t)in[i];
-}
-__global__ void k_narrow(const uint32_t* in, int32_t n, uint8_t* out) {
-  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (uint8_t)in[i];
+// d_ends / d_vals (device, SoA) -> pairs of store s on `stream`; *flag accumulates violations
+void launch_interleave(psk_store_s* s, const int32_t* d_ends, const void* d_vals, int64_t nruns, int32_t* flag,
+                       cudaStream_t stream) {
+  const unsigned grid = (unsigned)((nruns + 255) / 256);
+  if (elem_size(s->dtype) == 4)
+    PSK_LAUNCH(k_interleave<4>, grid, 256, 0, stream, d_ends, d_vals, (int32_t)nruns, s->d_runs, s->d_count, flag);
+  else if (s->dtype == PSK_BOOL)
+    PSK_LAUNCH(k_interleave<-1>, grid, 256, 0, stream, d_ends, d_vals, (int32_t)nruns, s->d_runs, s->d_count, flag);
+  else
+    PSK_LAUNCH(k_interleave<1>, grid, 256, 0, stream, d_ends, d_vals, (int32_t)nruns, s->d_runs, s->d_count, flag);
+  g.launches.fetch_add(1, std::memory_order_relaxed);
 }
 
-psk_status finish_runs_store(psk_store_s* s, int64_t nruns) {
-  // validate on device, fetch span (= last end)
-  int32_t* d_flag = nullptr;
-  psk_status st = dmalloc(reinterpret_cast<void**>(&d_flag), 8);
-  if (st != PSK_OK) return st;
-  CUDA_TRY(cudaMemsetAsync(d_flag, 0, 8, g.stream));
-  LAUNCH(k_validate_runs, (unsigned)((nruns + 255) / 256), 256, 0, s->d_ends, (int32_t)nruns, d_flag);
+// synchronous tail of the validated store constructors: read the flag and the span
+psk_status finish_runs_store(psk_store_s* s, int64_t nruns, int32_t* d_flag) {
   CUDA_TRY(cudaMemcpyAsync(g.h_ctrl, d_flag, 4, cudaMemcpyDeviceToHost, g.stream));
-  CUDA_TRY(cudaMemcpyAsync(g.h_ctrl + 1, s->d_ends + (nruns - 1), 4, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(g.h_ctrl + 1, &s->d_runs[nruns - 1].x, 4, cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   CUDA_TRY(cudaFreeAsync(d_flag, g.stream));
   if (g.h_ctrl[0] != 0) return fail(PSK_EINVAL, "run ends must be positive and strictly increasing");
@@ -343,7 +394,7 @@ psk_status finish_runs_store(psk_store_s* s, int64_t nruns) {
 namespace {
 template <int DT>
 psk_status encode_device(const void* d_dense, int64_t n, psk_store_t* out) {
-  // 16-byte accesses for 4-byte elements in an aligned buffer (psk_set_vector_conversion)
+  // 16-byte accesses for 4-byte elements in an aligned buffer
   const bool vec = g.convert_vec && (DT == PSK_I32 || DT == PSK_F32) &&
                    (reinterpret_cast<uintptr_t>(d_dense) & 15) == 0;
   const int32_t nb = (int32_t)((n + (vec ? kVecChunk : kConvChunk) - 1) / (vec ? kVecChunk : kConvChunk));
@@ -363,8 +414,9 @@ psk_status encode_device(const void* d_dense, int64_t n, psk_store_t* out) {
     cudaFreeAsync(d_counts, g.stream);
     return st;
   }
-  if (vec) LAUNCH(k_encode_write_vec<DT>, nb, kConvThreads, 0, d_dense, (long long)n, d_counts, s->d_ends, s->d_vals);
-  else LAUNCH(k_encode_write<DT>, nb, kConvThreads, 0, d_dense, (long long)n, d_counts, s->d_ends, s->d_vals);
+  if (vec) LAUNCH(k_encode_write_vec<DT>, nb, kConvThreads, 0, d_dense, (long long)n, d_counts, s->d_runs);
+  else LAUNCH(k_encode_write<DT>, nb, kConvThreads, 0, d_dense, (long long)n, d_counts, s->d_runs);
+  LAUNCH(k_seal, 1, 32, 0, s->d_runs, (int32_t)nruns, s->d_count);
   CUDA_TRY(cudaFreeAsync(d_counts, g.stream));
   s->nruns = nruns;
   s->span = (int32_t)n;
@@ -414,10 +466,11 @@ psk_status resolve(psk_store_s* s) {
   do {                                       \
     psk_status r_ = resolve(s);              \
     if (r_ != PSK_OK) return r_;             \
+    wait_ready(s);                           \
   } while (0)
 
 const char* psk_last_error(void) { return g_err.c_str(); }
-const char* psk_version(void) { return "pskb200 0.1 (sm_100a)"; }
+const char* psk_version(void) { return "pskb200 0.2 (sm_100a)"; }
 int32_t psk_is_simulator(void) {
 #ifdef PSK_CPU_SIM
   return 1;
@@ -507,13 +560,22 @@ psk_status psk_set_jit_threshold(int64_t min_total_runs) {
 
 int64_t psk_jit_launch_count(void) { return g.jit_launches; }
 
+psk_status psk_set_tile_geometry(int32_t threads, int32_t cap) {
+  std::lock_guard<std::recursive_mutex> api_lock_(g.api_mu);
+  PSK_CHECK_ARG(threads >= 32 && threads <= 1024 && threads % 32 == 0);
+  PSK_CHECK_ARG(cap >= 512 && cap <= 13000 && cap % 64 == 0);
+  g.jit_T = threads;
+  g.jit_CAP = cap;
+  return PSK_OK;
+}
+
 int32_t psk_jit_compile_check(int32_t k, int32_t nprog, const psk_node* prog, char* log, int32_t loglen) {
 #ifdef PSK_CPU_SIM
   (void)k; (void)nprog; (void)prog; (void)log; (void)loglen;
   return -1;
 #else
   if (validate_program(k, nprog, prog) != PSK_OK) return 2;
-  return jit_compile_check(k, false, nprog, prog, log, loglen);
+  return jit_compile_check(k, false, g.jit_T, g.jit_CAP, nprog, prog, log, loglen);
 #endif
 }
 
@@ -526,22 +588,6 @@ psk_status psk_profile(int32_t enable) {
 }
 
 #ifdef PSK_PHASE_TIMING
-// development builds only: per-tile globaltimer trace of the next evaluations
-PSK_API int32_t psk_trace_enable(int64_t max_tiles) {
-  if (ensure_init() != PSK_OK) return 1;
-  if (g.trace_buf) cudaFree(g.trace_buf);
-  g.trace_cap = max_tiles * 8;
-  if (cudaMalloc(reinterpret_cast<void**>(&g.trace_buf), (size_t)g.trace_cap * 8) != cudaSuccess) return 2;
-  cudaMemset(g.trace_buf, 0, (size_t)g.trace_cap * 8);
-  return 0;
-}
-PSK_API int64_t psk_trace_read(unsigned long long* out, int64_t cap_words) {
-  cudaStreamSynchronize(g.stream);
-  int64_t n = g.trace_tiles * 8;
-  if (n > cap_words) n = cap_words;
-  cudaMemcpy(out, g.trace_buf, (size_t)n * 8, cudaMemcpyDeviceToHost);
-  return g.trace_tiles;
-}
 // development builds only (tools/phase_profile.py); not part of include/pskb200.h
 PSK_API void psk_phase_read(unsigned long long* out8, int32_t reset) {
   for (int q = 0; q < 8; ++q) {
@@ -571,23 +617,26 @@ psk_status psk_store_from_runs(psk_dtype dtype, int64_t nruns, const int32_t* en
   psk_store_t s;
   psk_status st = new_store(dtype, nruns, &s);
   if (st != PSK_OK) return st;
-  cudaError_t e = cudaMemcpyAsync(s->d_ends, ends, (size_t)nruns * 4, cudaMemcpyHostToDevice, g.stream);
-  if (e == cudaSuccess) {
-    if (elem_size(dtype) == 4) {
-      e = cudaMemcpyAsync(s->d_vals, vals, (size_t)nruns * 4, cudaMemcpyHostToDevice, g.stream);
-    } else {
-      uint8_t* tmp = nullptr;
-      st = dmalloc(reinterpret_cast<void**>(&tmp), (size_t)nruns);
-      if (st == PSK_OK) {
-        e = cudaMemcpyAsync(tmp, vals, (size_t)nruns, cudaMemcpyHostToDevice, g.stream);
-        LAUNCH(k_widen, (unsigned)((nruns + 255) / 256), 256, 0, tmp, (int32_t)nruns, dtype == PSK_BOOL ? 1 : 0,
-               s->d_vals);
-        cudaFreeAsync(tmp, g.stream);
-      }
-    }
+  // staging: [flag | ends | vals] on the device, interleaved into the store by one kernel
+  const size_t vbytes = (size_t)nruns * elem_size(dtype);
+  const size_t o_ends = 16, o_vals = o_ends + (((size_t)nruns * 4 + 15) & ~(size_t)15);
+  unsigned char* tmp = nullptr;
+  st = dmalloc(reinterpret_cast<void**>(&tmp), o_vals + vbytes);
+  if (st != PSK_OK) {
+    psk_store_release(s);
+    return st;
   }
-  if (e != cudaSuccess) st = fail(PSK_ECUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
-  if (st == PSK_OK) st = finish_runs_store(s, nruns);
+  cudaError_t e = cudaMemsetAsync(tmp, 0, 16, g.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(tmp + o_ends, ends, (size_t)nruns * 4, cudaMemcpyHostToDevice, g.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(tmp + o_vals, vals, vbytes, cudaMemcpyHostToDevice, g.stream);
+  if (e != cudaSuccess) {
+    cudaFreeAsync(tmp, g.stream);
+    psk_store_release(s);
+    return fail(PSK_ECUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
+  }
+  launch_interleave(s, reinterpret_cast<int32_t*>(tmp + o_ends), tmp + o_vals, nruns, reinterpret_cast<int32_t*>(tmp),
+                    g.stream);
+  st = finish_runs_store(s, nruns, reinterpret_cast<int32_t*>(tmp));
   if (st != PSK_OK) {
     psk_store_release(s);
     return st;
@@ -608,15 +657,19 @@ psk_status psk_store_from_runs_async(psk_dtype dtype, int64_t nruns, const int32
   s->capacity = nruns;
   s->nruns = nruns;
   s->span = ends[nruns - 1];  // host memory: readable here
-  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&s->d_ends), (size_t)nruns * 4, g.h2d);
-  if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&s->d_vals), (size_t)nruns * 4, g.h2d);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_ends, ends, (size_t)nruns * 4, cudaMemcpyHostToDevice, g.h2d);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_vals, vals, (size_t)nruns * 4, cudaMemcpyHostToDevice, g.h2d);
+  // everything on the upload stream: staging, copies, interleave + validation
+  unsigned char* tmp = nullptr;
+  const size_t half = ((size_t)nruns * 4 + 15) & ~(size_t)15;
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&s->d_runs), (size_t)(nruns + kStorePad) * 8, g.h2d);
+  if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&tmp), 2 * half, g.h2d);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, ends, (size_t)nruns * 4, cudaMemcpyHostToDevice, g.h2d);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(tmp + half, vals, (size_t)nruns * 4, cudaMemcpyHostToDevice, g.h2d);
   if (e == cudaSuccess) {
-    PSK_LAUNCH(k_validate_runs, (unsigned)((nruns + 255) / 256), 256, 0, g.h2d, s->d_ends, (int32_t)nruns, g.d_async_err);
-    g.launches.fetch_add(1, std::memory_order_relaxed);
-    e = cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming);
+    s->d_count = reinterpret_cast<int32_t*>(s->d_runs + nruns + kStorePad - 1);
+    launch_interleave(s, reinterpret_cast<int32_t*>(tmp), tmp + half, nruns, g.d_async_err, g.h2d);
+    e = cudaFreeAsync(tmp, g.h2d);
   }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventRecord(s->ready, g.h2d);
   if (e != cudaSuccess) {
     delete s;
@@ -633,9 +686,21 @@ psk_status psk_store_runs_async(psk_store_t s, int32_t* ends, void* vals) {
   READY(s);
   PSK_CHECK_ARG(s->dtype == PSK_I32 || s->dtype == PSK_F32);
   const size_t n = (size_t)s->nruns;
+  // the download stream waits for everything queued on the library stream so far (the kernels
+  // that produce the store) and for the upload, if the store came from one
+  if (!g.xev) CUDA_TRY(cudaEventCreateWithFlags(&g.xev, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(g.xev, g.stream));
+  CUDA_TRY(cudaStreamWaitEvent(g.d2h, g.xev, 0));
   if (s->ready) CUDA_TRY(cudaStreamWaitEvent(g.d2h, s->ready, 0));
-  CUDA_TRY(cudaMemcpyAsync(ends, s->d_ends, n * 4, cudaMemcpyDeviceToHost, g.d2h));
-  CUDA_TRY(cudaMemcpyAsync(vals, s->d_vals, n * 4, cudaMemcpyDeviceToHost, g.d2h));
+  unsigned char* tmp = nullptr;
+  const size_t half = (n * 4 + 15) & ~(size_t)15;
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&tmp), 2 * half, g.d2h));
+  PSK_LAUNCH(k_deinterleave<4>, (unsigned)((n + 255) / 256), 256, 0, g.d2h, s->d_runs, (int32_t)n,
+             reinterpret_cast<int32_t*>(tmp), tmp + half);
+  g.launches.fetch_add(1, std::memory_order_relaxed);
+  CUDA_TRY(cudaMemcpyAsync(ends, tmp, n * 4, cudaMemcpyDeviceToHost, g.d2h));
+  CUDA_TRY(cudaMemcpyAsync(vals, tmp + half, n * 4, cudaMemcpyDeviceToHost, g.d2h));
+  CUDA_TRY(cudaFreeAsync(tmp, g.d2h));
   if (!s->busy) CUDA_TRY(cudaEventCreateWithFlags(&s->busy, cudaEventDisableTiming));
   CUDA_TRY(cudaEventRecord(s->busy, g.d2h));
   return PSK_OK;
@@ -657,11 +722,18 @@ psk_status psk_store_from_device_runs(psk_dtype dtype, int64_t nruns, const int3
   psk_store_t s;
   psk_status st = new_store(dtype, nruns, &s);
   if (st != PSK_OK) return st;
-  cudaError_t e = cudaMemcpyAsync(s->d_ends, d_ends, (size_t)nruns * 4, cudaMemcpyDeviceToDevice, g.stream);
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(s->d_vals, d_vals, (size_t)nruns * 4, cudaMemcpyDeviceToDevice, g.stream);
-  if (e != cudaSuccess) st = fail(PSK_ECUDA, std::string("D2D copy: ") + cudaGetErrorString(e));
-  if (st == PSK_OK) st = finish_runs_store(s, nruns);
+  int32_t* d_flag = nullptr;
+  st = dmalloc(reinterpret_cast<void**>(&d_flag), 16);
+  if (st != PSK_OK) {
+    psk_store_release(s);
+    return st;
+  }
+  cudaMemsetAsync(d_flag, 0, 16, g.stream);
+  // device payloads are always 32-bit words
+  PSK_LAUNCH(k_interleave<4>, (unsigned)((nruns + 255) / 256), 256, 0, g.stream, d_ends, (const void*)d_vals,
+             (int32_t)nruns, s->d_runs, s->d_count, d_flag);
+  g.launches.fetch_add(1, std::memory_order_relaxed);
+  st = finish_runs_store(s, nruns, d_flag);
   if (st != PSK_OK) {
     psk_store_release(s);
     return st;
@@ -678,13 +750,12 @@ psk_status psk_store_fill(psk_dtype dtype, int32_t span, uint32_t fill_bits, psk
   psk_store_t s;
   psk_status st = new_store(dtype, 1, &s);
   if (st != PSK_OK) return st;
-  LAUNCH(k_fill_one, 1, 32, 0, s->d_ends, s->d_vals, span, fill_bits);
+  LAUNCH(k_fill_one, 1, 32, 0, s->d_runs, s->d_count, span, fill_bits);
   s->nruns = 1;
   s->span = span;
   *out = s;
   return PSK_OK;
 }
-
 
 psk_status psk_store_from_dense_device(psk_dtype dtype, int64_t n, const void* d_dense, psk_store_t* out) {
   NEED_INIT();
@@ -727,15 +798,15 @@ psk_status psk_store_to_dense_device(psk_store_t s, void* d_out) {
   if (g.convert_vec && (s->dtype == PSK_I32 || s->dtype == PSK_F32) &&
       (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {
     // same block geometry, 16-byte stores (the two 4-byte types share the payload path)
-    LAUNCH(k_expand_vec<PSK_I32>, nb, kConvThreads, 0, s->d_ends, s->d_vals, (int32_t)s->nruns, n, d_out);
+    LAUNCH(k_expand_vec<PSK_I32>, nb, kConvThreads, 0, s->d_runs, (int32_t)s->nruns, n, d_out);
     CUDA_TRY(cudaGetLastError());
     return PSK_OK;
   }
   switch (s->dtype) {
-    case PSK_I32: LAUNCH(k_expand<PSK_I32>, nb, kConvThreads, 0, s->d_ends, s->d_vals, (int32_t)s->nruns, n, d_out); break;
-    case PSK_F32: LAUNCH(k_expand<PSK_F32>, nb, kConvThreads, 0, s->d_ends, s->d_vals, (int32_t)s->nruns, n, d_out); break;
-    case PSK_BOOL: LAUNCH(k_expand<PSK_BOOL>, nb, kConvThreads, 0, s->d_ends, s->d_vals, (int32_t)s->nruns, n, d_out); break;
-    default: LAUNCH(k_expand<PSK_CHAR>, nb, kConvThreads, 0, s->d_ends, s->d_vals, (int32_t)s->nruns, n, d_out); break;
+    case PSK_I32: LAUNCH(k_expand<PSK_I32>, nb, kConvThreads, 0, s->d_runs, (int32_t)s->nruns, n, d_out); break;
+    case PSK_F32: LAUNCH(k_expand<PSK_F32>, nb, kConvThreads, 0, s->d_runs, (int32_t)s->nruns, n, d_out); break;
+    case PSK_BOOL: LAUNCH(k_expand<PSK_BOOL>, nb, kConvThreads, 0, s->d_runs, (int32_t)s->nruns, n, d_out); break;
+    default: LAUNCH(k_expand<PSK_CHAR>, nb, kConvThreads, 0, s->d_runs, (int32_t)s->nruns, n, d_out); break;
   }
   CUDA_TRY(cudaGetLastError());
   return PSK_OK;
@@ -764,17 +835,17 @@ psk_status psk_store_runs(psk_store_t s, int32_t* ends, void* vals) {
   PSK_CHECK_ARG(s != nullptr && ends != nullptr && vals != nullptr);
   READY(s);
   const size_t n = (size_t)s->nruns;
-  CUDA_TRY(cudaMemcpyAsync(ends, s->d_ends, n * 4, cudaMemcpyDeviceToHost, g.stream));
-  if (elem_size(s->dtype) == 4) {
-    CUDA_TRY(cudaMemcpyAsync(vals, s->d_vals, n * 4, cudaMemcpyDeviceToHost, g.stream));
-  } else {
-    uint8_t* tmp = nullptr;
-    psk_status st = dmalloc(reinterpret_cast<void**>(&tmp), n);
-    if (st != PSK_OK) return st;
-    LAUNCH(k_narrow, (unsigned)((n + 255) / 256), 256, 0, s->d_vals, (int32_t)n, tmp);
-    CUDA_TRY(cudaMemcpyAsync(vals, tmp, n, cudaMemcpyDeviceToHost, g.stream));
-    CUDA_TRY(cudaFreeAsync(tmp, g.stream));
-  }
+  const size_t esz = (size_t)elem_size(s->dtype);
+  unsigned char* tmp = nullptr;
+  const size_t half = (n * 4 + 15) & ~(size_t)15;
+  psk_status st = dmalloc(reinterpret_cast<void**>(&tmp), half + n * esz);
+  if (st != PSK_OK) return st;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (esz == 4) LAUNCH(k_deinterleave<4>, grid, 256, 0, s->d_runs, (int32_t)n, reinterpret_cast<int32_t*>(tmp), tmp + half);
+  else LAUNCH(k_deinterleave<1>, grid, 256, 0, s->d_runs, (int32_t)n, reinterpret_cast<int32_t*>(tmp), tmp + half);
+  CUDA_TRY(cudaMemcpyAsync(ends, tmp, n * 4, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(vals, tmp + half, n * esz, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaFreeAsync(tmp, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   return PSK_OK;
 }
@@ -790,14 +861,13 @@ int64_t psk_store_nruns(psk_store_t s) {
 int32_t psk_store_span(psk_store_t s) { return s ? s->span : 0; }
 int32_t psk_store_dtype(psk_store_t s) { return s ? s->dtype : -1; }
 
-psk_status psk_store_device_ptrs(psk_store_t s, const int32_t** d_ends, const uint32_t** d_vals) {
-  PSK_CHECK_ARG(s != nullptr && d_ends != nullptr && d_vals != nullptr);
-  if (s->pending_slot >= 0 || s->failed) {
+psk_status psk_store_device_pairs(psk_store_t s, const void** d_pairs) {
+  PSK_CHECK_ARG(s != nullptr && d_pairs != nullptr);
+  {
     std::lock_guard<std::recursive_mutex> api_lock_(g.api_mu);
     READY(s);
   }
-  *d_ends = s->d_ends;
-  *d_vals = s->d_vals;
+  *d_pairs = s->d_runs;
   return PSK_OK;
 }
 
@@ -805,7 +875,7 @@ psk_status psk_store_first_value(psk_store_t s, uint32_t* bits) {
   NEED_INIT();
   PSK_CHECK_ARG(s != nullptr && bits != nullptr);
   READY(s);
-  CUDA_TRY(cudaMemcpyAsync(g.h_ctrl, s->d_vals, 4, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(g.h_ctrl, &s->d_runs[0].y, 4, cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   *bits = (uint32_t)g.h_ctrl[0];
   return PSK_OK;
@@ -815,8 +885,8 @@ psk_status psk_store_boundary(psk_store_t s, uint32_t* first_bits, uint32_t* las
   NEED_INIT();
   PSK_CHECK_ARG(s != nullptr && first_bits != nullptr && last_bits != nullptr && nruns != nullptr);
   READY(s);
-  CUDA_TRY(cudaMemcpyAsync(g.h_ctrl, s->d_vals, 4, cudaMemcpyDeviceToHost, g.stream));
-  CUDA_TRY(cudaMemcpyAsync(g.h_ctrl + 1, s->d_vals + (s->nruns - 1), 4, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(g.h_ctrl, &s->d_runs[0].y, 4, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(g.h_ctrl + 1, &s->d_runs[s->nruns - 1].y, 4, cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   *first_bits = (uint32_t)g.h_ctrl[0];
   *last_bits = (uint32_t)g.h_ctrl[1];
@@ -827,11 +897,11 @@ psk_status psk_store_boundary(psk_store_t s, uint32_t* first_bits, uint32_t* las
 psk_status psk_store_boundary_device(psk_store_t s, int64_t* d_out3) {
   NEED_INIT();
   PSK_CHECK_ARG(s != nullptr && d_out3 != nullptr);
-  // a deferred result is NOT completed here: the kernel reads its run count from the spare
-  // word behind the ends, so the caller's pipeline stays asynchronous
-  const int32_t* d_count = s->pending_slot >= 0 ? s->d_ends + s->capacity : nullptr;
+  // a deferred result is NOT completed here: the kernel reads its run count from the device
+  // word of the store, so the caller's pipeline stays asynchronous
+  const int32_t* d_count = s->pending_slot >= 0 ? s->d_count : nullptr;
   if (!d_count) READY(s);
-  LAUNCH(k_boundary, 1, 32, 0, s->d_vals, (int64_t)s->nruns, d_count, reinterpret_cast<long long*>(d_out3));
+  LAUNCH(k_boundary, 1, 32, 0, s->d_runs, (int64_t)s->nruns, d_count, reinterpret_cast<long long*>(d_out3));
   return PSK_OK;
 }
 
@@ -842,15 +912,13 @@ void psk_store_retain(psk_store_t s) {
 void psk_store_release(psk_store_t s) {
   if (!s) return;
   if (s->ref.fetch_sub(1) == 1) {
-    if (s->pending_slot >= 0) {  // result never looked at
-      std::lock_guard<std::recursive_mutex> api_lock_(g.api_mu);
-      g.slots[s->pending_slot].owner = nullptr;
-    }
+    std::lock_guard<std::recursive_mutex> api_lock_(g.api_mu);
+    const int32_t slot = s->pending_slot;  // result never looked at
+    if (slot >= 0 && slot < Ctx::kAsyncSlots && g.slots[slot].owner == s) g.slots[slot].owner = nullptr;
     // stream-ordered free on the library stream, after any copy still reading / writing it
     if (s->ready) { cudaStreamWaitEvent(g.stream, s->ready, 0); cudaEventDestroy(s->ready); }
     if (s->busy) { cudaStreamWaitEvent(g.stream, s->busy, 0); cudaEventDestroy(s->busy); }
-    if (s->d_ends) cudaFreeAsync(s->d_ends, g.stream);
-    if (s->d_vals) cudaFreeAsync(s->d_vals, g.stream);
+    if (s->d_runs) cudaFreeAsync(s->d_runs, g.stream);
     g.live_bytes -= s->capacity * 8;
     delete s;
   }
@@ -886,7 +954,10 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
   if (st != PSK_OK) return st;
   for (int i = 0; i < k; ++i) {
     PSK_CHECK_ARG(sources[i].store != nullptr);
-    READY(sources[i].store);  // a source that is itself a deferred result: its run count is needed
+    // a source that is itself a queued result is NOT waited for: its run count is read on the
+    // device (k_prepare) and everything here is sized by its capacity.  Only a result that
+    // already failed is reported.
+    if (sources[i].store->failed) READY(sources[i].store);
   }
 #ifdef PSK_PHASE_TIMING
   deferred = false;
@@ -904,20 +975,21 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
   hp.k = k;
   hp.eq = (eq == PSK_EQ_TYPED && out_dtype == PSK_F32) ? 1 : 0;
   hp.nprog = nprog;
+  hp.epoch = 0;
   memcpy(hp.prog, prog, sizeof(psk_node) * (size_t)nprog);
 
   int64_t span = -1;
-  int64_t total_runs = 0;
-  bool any_views = false;
+  int64_t total_runs = 0;  // upper bound when a source is a queued result
+  bool any_views = false, any_queued = false;
   bool used_async = false;
   for (int i = 0; i < k; ++i) {
     const psk_source& s = sources[i];
-    PSK_CHECK_ARG(s.store != nullptr);
     PSK_CHECK_ARG(s.nviews >= 0 && s.nviews <= PSK_MAX_VIEWS);
     DSource& d = hp.src[i];
-    d.ends = s.store->d_ends;
-    d.vals = s.store->d_vals;
-    d.nruns = (int32_t)s.store->nruns;
+    d.runs = s.store->d_runs;
+    const bool queued = s.store->pending_slot >= 0;
+    d.d_count = queued ? s.store->d_count : nullptr;
+    d.nruns = (int32_t)(queued ? s.store->capacity : s.store->nruns);
     d.nviews = s.nviews;
     int64_t cur = s.store->span;
     for (int v = 0; v < s.nviews; ++v) {
@@ -929,10 +1001,9 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
       cur = o;
     }
     if (s.nviews) any_views = true;
+    if (queued) any_queued = true;
     if (s.store->ready) {  // uploaded by psk_store_from_runs_async: order the kernels after the copy
-      CUDA_TRY(cudaStreamWaitEvent(g.stream, s.store->ready, 0));
-      cudaEventDestroy(s.store->ready);
-      s.store->ready = nullptr;
+      wait_ready(s.store);
       used_async = true;
     }
     // every source of a pool must share the output span (eval.hpp:400-403, lang.hpp:198)
@@ -944,17 +1015,37 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
   PSK_CHECK_ARG(total_runs < 0x7ffffff0LL);
   hp.span = (int32_t)span;
   hp.any_views = any_views ? 1 : 0;
-  hp.stagger_ns = g.stagger_ns;
+  const bool on_device = any_views || any_queued;
+  hp.on_device = on_device ? 1 : 0;
 
-  // ---- partition parameters: S * (m + 2k) <= kTileCap bounds the runs of one tile --------
-  // (the rank-merge of the samples costs O(samples * k * log): keep S at 64 for wide steps)
-  int S = k <= 4 ? 256 : k <= 8 ? 128 : 64;
-  while (S > 32 && total_runs / S < 2048) S >>= 1;
+  // ---- which kernel: the specialised one (NVRTC) for large evaluations ---------------------
+  int T = kTileThreads, CAP = kTileCap;
+#ifndef PSK_CPU_SIM
+  const JitKernel* jk = nullptr;
+  if (total_runs >= g.jit_min_runs) {
+    // K = k exactly: no padding sources in the specialised kernel
+    jk = jit_get_merge_eval(k, hp.eq != 0, any_views, g.jit_T, g.jit_CAP, nprog, prog, nullptr);
+    if (jk) {
+      T = g.jit_T;
+      CAP = g.jit_CAP;
+    }
+  }
+#endif
+  const size_t smem = 2u * (size_t)(CAP + kTileSlack) * 8u;
+  int ctas = (int)((227 * 1024) / (smem + 5120));
+  if (ctas > 2048 / T) ctas = 2048 / T;
+  if (ctas < 1) ctas = 1;
+
+  // ---- partition parameters: S * (m + 2k) <= CAP bounds the runs of one tile ---------------
+  int S = CAP / 32;
+  if (k > 8) S = CAP / 64;
+  while (S > 16 && total_runs / S < 1024) S >>= 1;
+  while (S > 4 && CAP / S - 2 * k < 4) S >>= 1;
   int64_t max_samples = 0;
   for (int i = 0; i < k; ++i) max_samples += (hp.src[i].nruns + S - 1) / S;
-  const int m_max = kTileCap / S - 2 * k;
-  int m = (int)(max_samples / (2 * (int64_t)g.sm_count));  // aim at >= 2 tiles per SM ...
-  const int m_small = 2048 / S;                            // ... but not at tiles below ~2k runs
+  const int m_max = CAP / S - 2 * k;
+  int m = (int)(max_samples / (2 * (int64_t)ctas * g.sm_count));  // aim at >= 2 tiles per resident CTA ...
+  const int m_small = (CAP / 4) / S;                              // ... but not at tiles below CAP/4 runs
   if (m < m_small) m = m_small;
   if (m > m_max) m = m_max;
   if (m < 1) m = 1;
@@ -962,7 +1053,7 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
   hp.S = S;
   hp.m = m;
   hp.max_tiles = (int32_t)max_tiles;
-  if (!any_views) {
+  {
     int32_t off = 0;
     for (int i = 0; i < k; ++i) {
       DSource& d = hp.src[i];
@@ -974,20 +1065,17 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
     }
     hp.total_samples = off;
     hp.n_tiles = (off + m - 1) / m;
-  } else {
-    hp.total_samples = 0;
-    hp.n_tiles = 0;
+    if (hp.n_tiles < 1) hp.n_tiles = 1;
   }
 
-  // ---- scratch: [tile_state | ctrl | merged | samp_keys | bounds | tile_hi | plan] ---------
+  // ---- scratch: [tile_state | phase | ctrl | bounds | tile_hi | lookahead | plan] ------------
   size_t o_state = 0;
   size_t o_phase = o_state + (size_t)max_tiles * 8;
   size_t o_ctrl = o_phase + 8 * 8;
-  size_t o_merged = o_ctrl + CTRL_WORDS * 4;
-  size_t o_keys = o_merged + (size_t)max_samples * 4;
-  size_t o_bounds = o_keys + (size_t)max_samples * 4;
+  size_t o_bounds = o_ctrl + CTRL_WORDS * 4;
   size_t o_hi = o_bounds + (size_t)(max_tiles + 1) * k * 4;
-  size_t o_plan = (o_hi + (size_t)max_tiles * 4 + 15) & ~(size_t)15;
+  size_t o_la = (o_hi + (size_t)max_tiles * 4 + 15) & ~(size_t)15;
+  size_t o_plan = (o_la + (any_views ? (size_t)max_tiles * k * 16 : 0) + 15) & ~(size_t)15;
   const size_t plan_bytes = offsetof(DPlan, src) + sizeof(DSource) * (size_t)k;
   size_t scratch_bytes = o_plan + sizeof(DPlan);
   unsigned char* scratch = nullptr;
@@ -1003,71 +1091,46 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
   hp.ctrl = reinterpret_cast<int32_t*>(scratch + o_ctrl);
   hp.phase = reinterpret_cast<unsigned long long*>(scratch + o_phase);
   hp.trace = nullptr;
-#ifdef PSK_PHASE_TIMING
-  if (g.trace_buf && max_tiles * 8 <= g.trace_cap) {
-    hp.trace = g.trace_buf;
-    g.trace_tiles = max_tiles;
-  }
-#endif
-  hp.merged = reinterpret_cast<int32_t*>(scratch + o_merged);
-  hp.samp_keys = reinterpret_cast<int32_t*>(scratch + o_keys);
   hp.bounds = reinterpret_cast<int32_t*>(scratch + o_bounds);
   hp.tile_hi = reinterpret_cast<int32_t*>(scratch + o_hi);
-  hp.out_ends = res->d_ends;
-  hp.out_vals = res->d_vals;
+  hp.lookahead = reinterpret_cast<int2*>(scratch + o_la);
+  hp.out = res->d_runs;
+  hp.out_count = res->d_count;
   hp.out_capacity = (int32_t)total_runs;
   DPlan* d_plan = reinterpret_cast<DPlan*>(scratch + o_plan);
-  // small evaluation without views: one tile holds every run (+ one look-ahead slot per source)
-  const bool single_tile = !any_views && total_runs + k <= kTileCap && g.small_partition > 0;
-  if (single_tile) {
-    for (int i = 0; i < k; ++i) {
-      hp.one_bounds[i] = 0;
-      hp.one_bounds[k + i] = hp.src[i].nruns;
-    }
-    hp.one_hi = (int32_t)span;
-    hp.n_tiles = 1;
-    hp.bounds = d_plan->one_bounds;   // device addresses inside the uploaded plan
-    hp.tile_hi = &d_plan->one_hi;
-  }
 
-  cudaError_t e = cudaMemsetAsync(scratch, 0, o_merged, g.stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_plan, &hp, plan_bytes, cudaMemcpyHostToDevice, g.stream);
+  cudaError_t e = cudaMemcpyAsync(d_plan, &hp, plan_bytes, cudaMemcpyHostToDevice, g.stream);
+#ifdef PSK_PHASE_TIMING
+  if (e == cudaSuccess) e = cudaMemsetAsync(hp.phase, 0, 64, g.stream);
+#endif
   if (e == cudaSuccess) {
-    if (!single_tile && max_samples <= g.small_partition) {
-      // few samples: prepare + keys + rank + bounds in one block
-      LAUNCH(k_partition_small, 1, 1024, 0, d_plan, any_views ? 1 : 0);
-    } else if (!single_tile) {
-      if (any_views) LAUNCH(k_prepare, 1, 32 * k, 0, d_plan);
-      LAUNCH(k_sample_keys, (unsigned)((max_samples + 255) / 256), 256, 0, d_plan);
-      LAUNCH(k_sample_rank, (unsigned)((max_samples + kRankBlock - 1) / kRankBlock), kRankBlock, 0, d_plan);
-      LAUNCH(k_tile_bounds, (unsigned)(((max_tiles + 1) * k + 255) / 256), 256, 0, d_plan);
-    }
+    if (on_device) LAUNCH(k_prepare, 1, 32 * k, 0, d_plan);
+    int64_t pgrid = (max_samples + kPartBlock - 1) / kPartBlock;
+    if (pgrid < 1) pgrid = 1;
+    LAUNCH(k_partition, (unsigned)pgrid, kPartBlock, 0, d_plan);
     // persistent grid: as many CTAs as stay resident (shared memory / thread limits)
-    int64_t grid = kCtasPerSm * (int64_t)g.sm_count;
+    int64_t grid = (int64_t)ctas * g.sm_count;
     if (grid > max_tiles) grid = max_tiles;
-    if (single_tile) grid = 1;
     if (g.profile) cudaEventRecord(deferred ? g.slots[slot].t0 : g.pev0, g.stream);
     bool launched = false;
 #ifndef PSK_CPU_SIM
-    if (total_runs >= g.jit_min_runs) {
-      // the same kernel template with the program compiled in (psk_jit.h)
-      // K = k exactly: no padding sources in the specialised kernel
-      if (const JitKernel* jk = jit_get_merge_eval(k, hp.eq != 0, any_views, nprog, prog, nullptr)) {
-        if (jit_launch(jk, (unsigned)grid, kTileThreads, kMergeEvalSmemBytes, g.stream, d_plan) == 0) {
-          launched = true;
-          g.launches.fetch_add(1, std::memory_order_relaxed);
-          g.jit_launches += 1;
-        }
+    if (jk) {
+      if (jit_launch(jk, (unsigned)grid, (unsigned)T, smem, g.stream, d_plan) == 0) {
+        launched = true;
+        g.launches.fetch_add(1, std::memory_order_relaxed);
+        g.jit_launches += 1;
+      } else {
+        e = cudaErrorUnknown;  // the partition was laid out for the specialised kernel's tiles
       }
     }
 #endif
-    if (!launched) launch_merge_eval(pick_K(k), (int)grid, d_plan);
+    if (!launched && e == cudaSuccess) launch_merge_eval(pick_K(k), (int)grid, d_plan);
     if (g.profile) cudaEventRecord(deferred ? g.slots[slot].t1 : g.pev1, g.stream);
     if (deferred) {
       g.slots[slot].timed = g.profile;
       g.slots[slot].runs_in = total_runs;
     }
-    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
   }
   if (deferred) {
     int32_t* w = g.h_async + 8 * slot;
@@ -1173,7 +1236,7 @@ psk_status psk_mask_nd(int32_t ndim, const int32_t* shape, const int32_t* start,
   psk_store_t raw;
   st = new_store(PSK_BOOL, nraw, &raw);
   if (st != PSK_OK) return st;
-  LAUNCH(k_mask_segments, (unsigned)((nseg + 255) / 256), 256, 0, d, seg_len, (int32_t)nseg, raw->d_ends, raw->d_vals);
+  LAUNCH(k_mask_segments, (unsigned)((nseg + 255) / 256), 256, 0, d, seg_len, (int32_t)nseg, raw->d_runs);
   raw->nruns = nraw;
   raw->span = (int32_t)d.n;
   psk_source src;
@@ -1195,19 +1258,25 @@ psk_status psk_mask_nd(int32_t ndim, const int32_t* shape, const int32_t* start,
 psk_status psk_reduce(psk_store_t s, psk_reduce_op op, uint64_t* result_bits) {
   NEED_INIT();
   PSK_CHECK_ARG(s != nullptr && result_bits != nullptr);
-  READY(s);
   PSK_CHECK_ARG(op >= PSK_RED_SUM && op <= PSK_RED_PROD);
+  // a queued result is reduced without completing it first: the kernel reads its run count
+  // on the device and the grid is sized by the capacity
+  const bool queued = s->pending_slot >= 0 && !s->failed;
+  if (!queued) READY(s);
+  const int64_t nmax = queued ? s->capacity : s->nruns;
   const bool is_f = s->dtype == PSK_F32;
-  int nblocks = (int)((s->nruns + kRedThreads - 1) / kRedThreads);
+  int nblocks = (int)((nmax + kRedThreads - 1) / kRedThreads);
   if (nblocks > kRedBlocks) nblocks = kRedBlocks;
+  if (nblocks < 1) nblocks = 1;
   RedAcc* d_part = nullptr;
   psk_status st = dmalloc(reinterpret_cast<void**>(&d_part), sizeof(RedAcc) * (size_t)(nblocks + 1));
   if (st != PSK_OK) return st;
+  const int32_t* d_count = queued ? s->d_count : nullptr;
   if (is_f) {
-    LAUNCH(k_reduce_partial<true>, nblocks, kRedThreads, 0, s->d_ends, s->d_vals, (int32_t)s->nruns, (int)op, d_part);
+    LAUNCH(k_reduce_partial<true>, nblocks, kRedThreads, 0, s->d_runs, (int32_t)nmax, d_count, (int)op, d_part);
     LAUNCH(k_reduce_final<true>, 1, kRedThreads, 0, d_part, nblocks, (int)op, d_part + nblocks);
   } else {
-    LAUNCH(k_reduce_partial<false>, nblocks, kRedThreads, 0, s->d_ends, s->d_vals, (int32_t)s->nruns, (int)op, d_part);
+    LAUNCH(k_reduce_partial<false>, nblocks, kRedThreads, 0, s->d_runs, (int32_t)nmax, d_count, (int)op, d_part);
     LAUNCH(k_reduce_final<false>, 1, kRedThreads, 0, d_part, nblocks, (int)op, d_part + nblocks);
   }
   RedAcc* h = reinterpret_cast<RedAcc*>(g.h_ctrl);
@@ -1224,7 +1293,6 @@ psk_status psk_reduce(psk_store_t s, psk_reduce_op op, uint64_t* result_bits) {
 psk_status psk_store_slice(psk_store_t s, int32_t start, int32_t stop, psk_store_t* out) {
   NEED_INIT();
   PSK_CHECK_ARG(s != nullptr && out != nullptr);
-  READY(s);
   PSK_CHECK_ARG(0 <= start && start < stop && stop <= s->span);
   psk_source src;
   memset(&src, 0, sizeof(src));
