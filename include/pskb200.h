@@ -184,10 +184,12 @@ PSK_API psk_status psk_set_vector_conversion(int32_t enable);
  * `prog` over k sources compiles to an sm_100a cubin; the compiler log goes to `log`. */
 PSK_API int32_t psk_jit_compile_check(int32_t k, int32_t nprog, const psk_node* prog, char* log,
                                       int32_t loglen);
-/* Tuning aid: tile geometry of the specialised kernels -- threads per CTA (multiple of 32) and
- * runs per tile (multiple of 64).  The partition and the number of resident CTAs follow.
- * Results do not depend on it.  Also read once from PSKB200_TILE_THREADS / PSKB200_TILE_CAP. */
-PSK_API psk_status psk_set_tile_geometry(int32_t threads, int32_t cap);
+/* Tuning aid: tile geometry of the specialised kernels -- threads per CTA (multiple of 32),
+ * runs per tile (multiple of 64) and shared-memory regions (2: a tile's spans are written out
+ * while the next tile is being prepared; 3: one tile later).  The partition and the number of
+ * resident CTAs follow.  Results do not depend on it.  Also read once from
+ * PSKB200_TILE_THREADS / PSKB200_TILE_CAP / PSKB200_TILE_REGIONS. */
+PSK_API psk_status psk_set_tile_geometry(int32_t threads, int32_t cap, int32_t regions);
 /* How many psk_eval calls ran on a specialised kernel. */
 PSK_API int64_t psk_jit_launch_count(void);
 /* Measurement aid for bench.py's roofline line: when enabled, psk_eval brackets its
@@ -261,6 +263,22 @@ PSK_API psk_status psk_eval_async(int32_t k, const psk_source* sources, int32_t 
 /* Output span of a source view chain applied to a store span (lang::slice, lang.hpp:162). */
 PSK_API psk_status psk_view_span(int32_t span_in, int32_t nviews, const psk_view* views,
                                  int32_t* span_out);
+
+/* ---- stencil over runs: conv_2d / conv_3d (src/pyskip/convolve.py:5-59) -----------------
+ * Cross-correlation (no flip) of an N-D tensor (ndim 2 or 3, shape[] with dim 0 fastest, held
+ * as the flat store `s`) with a dense kernel of kshape[], weights[] in the same layout (x
+ * fastest: weights[a + KW*(b + KH*c)] = kernel[a, b, c]), after padding every side of dim i
+ * with pad[i] elements of `fill_bits`; output extent per dim = shape + 2*pad - kshape + 1.
+ * Values are those of the reference's tap loop (convolve.py:52-58: out = 0, then
+ * out += kernel[x,y,z] * window, z outer / x inner; int32 wraps, float32 rounds after every
+ * multiply and every add); the result is the canonical store under `eq`.  One kernel walks the
+ * taps as shifted windows of the same rows; nothing padded is materialised.
+ * psk_conv_supported: 1 when the stencil kernel handles this kernel shape (3x3, 3x3x3);
+ * other shapes go through psk_eval with gather views, as the reference does. */
+PSK_API int32_t psk_conv_supported(int32_t ndim, const int32_t* kshape);
+PSK_API psk_status psk_conv_nd(psk_store_t s, int32_t ndim, const int32_t* shape,
+                               const int32_t* kshape, const uint32_t* weights, const int32_t* pad,
+                               uint32_t fill_bits, psk_eq eq, psk_store_t* out);
 
 /* ---- masks: TensorSlice::mask / mask::stride_mask (tensor.hpp:171-198, mask.hpp:184-200)
  * RLE indicator (BOOL) of the positions a strided box selects, generated on device. */

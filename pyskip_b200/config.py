@@ -5,7 +5,9 @@ which an array is evaluated eagerly; reference array.hpp:210) and ``gpu_eval_max
 (sources merged per kernel launch, 2..30, default 8: wider expressions run as a chain of
 launches because the k-way merge step costs O(k) per run).  ``accelerated_eval``,
 ``parallelize_threshold`` and ``parallelize_parts`` are accepted for compatibility and have
-no effect (they select CPU code paths; results never depended on them)."""
+no effect (they select CPU code paths; results never depended on them).
+``conv_stencil_kernel`` (bool, default True): run 3x3 / 3x3x3 convolutions on the one-pass
+stencil-over-runs kernel instead of the tap loop (same results)."""
 from contextlib import contextmanager
 
 from . import _pyskip_b200_ext as _ext
@@ -16,6 +18,11 @@ _cfg = _ext.config
 
 def get_all_values():
     return _cfg.get_all_values()
+
+
+def get_config_value(name, default=None):
+    """Current value of a config key (or `default` when it is not set)."""
+    return _cfg.get_all_values().get(name, default)
 
 
 def set_value(name, val):

@@ -9,7 +9,8 @@ read back once, and the whole tap sum is built lazily and evaluated in as few la
 planner's width limit allows (27 taps of a 3x3x3 kernel = one k-way merge launch)."""
 import numpy as np
 
-from .config import lazy_evaluation_scope
+from . import _pyskip_b200_ext as _ext
+from .config import get_config_value, lazy_evaluation_scope
 from .tensor import Tensor
 from .util import broadcast_shape
 
@@ -28,9 +29,30 @@ def pad_3d_tensor(tensor, padding, fill):
     return _pad(tensor, broadcast_shape(3, padding), fill)
 
 
+def _conv_stencil(tensor, kernel, pads, fill):
+    """One launch of the stencil-over-runs kernel (psk_conv_nd) when it handles this kernel
+    shape; None otherwise.  Same values and run structure as the tap loop below."""
+    if tensor.dtype not in (int, float) or kernel.dtype != tensor.dtype:
+        return None
+    out_shape = tuple(s + 2 * p - k + 1 for s, p, k in zip(tensor.shape, pads, kernel.shape))
+    if any(o <= 0 for o in out_shape):
+        return None
+    weights = np.ascontiguousarray(kernel.to_numpy()).ravel()     # numpy C order = pyskip x fastest
+    weights = weights.astype(np.int32 if tensor.dtype is int else np.float32)
+    flat = _ext._conv_nd(tensor._tensor.array(), list(tensor.shape), list(kernel.shape), weights, list(pads),
+                         tensor.dtype(fill))
+    if flat is None:
+        return None
+    return Tensor(shape=out_shape, dtype=tensor.dtype, val=flat)
+
+
 def _conv(tensor, kernel, padding, fill):
     nd = tensor.ndim
     pads = broadcast_shape(nd, padding)
+    if get_config_value("conv_stencil_kernel", True):
+        out = _conv_stencil(tensor, kernel, pads, fill)
+        if out is not None:
+            return out
     s = _pad(tensor, pads, fill)
     kshape = kernel.shape
     out_shape = tuple(a - k + 1 for a, k in zip(s.shape, kshape))

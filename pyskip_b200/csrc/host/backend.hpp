@@ -37,6 +37,9 @@ struct Backend {
   PSK_FN(psk_view_span)
   PSK_FN(psk_mask_nd)
   PSK_FN(psk_reduce)
+  PSK_FN(psk_conv_supported)
+  PSK_FN(psk_conv_nd)
+  PSK_FN(psk_eval_async)
 #undef PSK_FN
 };
 
@@ -78,6 +81,9 @@ inline void bind_backend(const std::string& path, bool rebind) {
   PSK_FN(psk_view_span)
   PSK_FN(psk_mask_nd)
   PSK_FN(psk_reduce)
+  PSK_FN(psk_conv_supported)
+  PSK_FN(psk_conv_nd)
+  PSK_FN(psk_eval_async)
 #undef PSK_FN
   b = nb;
 }

@@ -298,6 +298,28 @@ void type_binds(py::module& m, const std::string& friendly, const std::string& p
   m.def("from_numpy", [](py::array_t<T, py::array::c_style | py::array::forcecast>& array) {
     return wrap<DT>(Array::from_dense(DT, array.size(), array.data()));
   });
+  // stencil-over-runs convolution (psk_conv_nd): `weights` is the dense kernel flattened in
+  // pyskip order (x fastest); returns the flat result array, or None when the kernel shape is
+  // not one the stencil kernel handles (the caller then runs the reference's tap loop)
+  if (DT == PSK_I32 || DT == PSK_F32) {
+    m.def("_conv_nd", [](const TArray<DT>& a, const std::vector<int32_t>& shape, const std::vector<int32_t>& kshape,
+                         py::array_t<T, py::array::c_style | py::array::forcecast>& weights,
+                         const std::vector<int32_t>& pads, typename CType<DT>::py_scalar fill) -> py::object {
+      const int nd = (int)shape.size();
+      PSK_CHECK_ARGUMENT((int)kshape.size() == nd && (int)pads.size() == nd);
+      if (!backend().psk_conv_supported(nd, kshape.data())) return py::none();
+      int64_t taps = 1;
+      for (int v : kshape) taps *= v;
+      PSK_CHECK_ARGUMENT(weights.size() == taps);
+      std::vector<uint32_t> w((size_t)taps);
+      memcpy(w.data(), weights.data(), (size_t)taps * 4);
+      StoreRef st = a.a.eval().store();
+      psk_store_t h = nullptr;
+      check(backend().psk_conv_nd(st.get(), nd, shape.data(), kshape.data(), w.data(), pads.data(),
+                                  bits_of(DT, from_py_scalar<DT>(fill)), PSK_EQ_BITWISE, &h));
+      return py::cast(wrap<DT>(Array::from_store(StoreRef(h))));
+    });
+  }
 }
 
 }  // namespace

@@ -48,14 +48,19 @@ namespace psk {
 constexpr int kTileThreads = PSK_TILE_THREADS;
 constexpr int kTileCap = PSK_TILE_CAP;  // in-tile runs of all sources together
 constexpr int kSentinel = 0x7fffffff;
+constexpr int kStateStride = 4;  // 64-bit words per look-back entry (one 32-byte sector per tile)
 // per source beyond its in-tile runs: two look-ahead runs + up to two pairs of 16-byte alignment
 constexpr int kTileSlack = 4 * PSK_MAX_SOURCES;
 constexpr int kTileRegion = kTileCap + kTileSlack;  // pairs per shared-memory region
 
-// dynamic shared memory of k_merge_eval: region A | region B (8-byte pairs)
-constexpr unsigned kMergeEvalSmemBytes = 2u * kTileRegion * 8u;
+// dynamic shared memory of k_merge_eval: regions A | B (| C) of 8-byte pairs
+#ifndef PSK_TILE_REGIONS
+#define PSK_TILE_REGIONS 2
+#endif
+constexpr int kTileRegions = PSK_TILE_REGIONS;  // 2: A + B; 3: A + B + C (spans parked for a whole tile)
+constexpr unsigned kMergeEvalSmemBytes = (unsigned)kTileRegions * kTileRegion * 8u;
 // CTAs that stay resident per SM (227 KB of shared memory, 2048 threads)
-constexpr int kCtasBySmem = (227 * 1024) / (int)(kMergeEvalSmemBytes + 5120);
+constexpr int kCtasBySmem = (227 * 1024) / (int)(kMergeEvalSmemBytes + 6144);
 constexpr int kCtasByThreads = 2048 / kTileThreads;
 constexpr int kCtasPerSm = kCtasBySmem < kCtasByThreads ? (kCtasBySmem < 1 ? 1 : kCtasBySmem) : kCtasByThreads;
 
@@ -231,7 +236,7 @@ __global__ void __launch_bounds__(kPartBlock) k_partition(DPlan* p) {
 
   // housekeeping that would otherwise be memsets: look-back words, control words, the
   // first and last rows of the bounds table
-  for (int32_t t = blockIdx.x * kPartBlock + tid; t < p->max_tiles; t += gridDim.x * kPartBlock)
+  for (int32_t t = blockIdx.x * kPartBlock + tid; t < p->max_tiles * kStateStride; t += gridDim.x * kPartBlock)
     p->tile_state[t] = 0ull;
   if (blockIdx.x == 0) {
     if (tid < CTRL_WORDS) p->ctrl[tid] = 0;
@@ -444,55 +449,103 @@ PSK_D int32_t block_exclusive_scan(int32_t v, int32_t* s_warp /*[T/32+1]*/, int3
   return excl;
 }
 
+// One look-back entry per tile, padded to a 32-byte sector: hundreds of resident CTAs read the
+// entries of the tiles in front of them at the same time.
 PSK_D void publish_aggregate(unsigned long long* state, int32_t tile, int32_t count) {
   // tile 0 has no predecessor: its aggregate is already its inclusive prefix
   const unsigned long long st = tile == 0 ? ST_PREFIX : ST_AGGREGATE;
-  st_volatile_u64(&state[tile], (st << 32) | (uint32_t)count);
+  st_volatile_u64(&state[(long long)tile * kStateStride], (st << 32) | (uint32_t)count);
 }
 
-// Decoupled look-back, executed by the whole CTA: thread r inspects tile (j - r), so one
-// round covers T predecessors.  The nearest tile that already published an inclusive PREFIX
-// ends the walk.  Tiles are handed out by an atomic ticket, so every predecessor is resident
-// or finished and the spin cannot deadlock.  Status and count travel in ONE 64-bit word, so
-// no ordering between separate words is needed.
+// Decoupled look-back, executed by the whole CTA.  Thread r loads the entries of the tiles at
+// distances r+1, r+1+T, ... in front of `tile` -- kLookW independent loads, one memory round
+// trip for T * kLookW predecessors, which normally covers every tile that can still be in
+// flight.  The loads are ISSUED early (lookback_issue, right after the tile's own aggregate
+// is published) and consumed later (lookback_finish, after the next tile has been searched),
+// so their latency never shows; an entry that is still empty then is polled with back-off.
+// The block folds in tile order: the nearest tile with an inclusive PREFIX ends the sum,
+// everything nearer contributes its AGGREGATE.  Tiles are handed out by an atomic ticket, so
+// every predecessor is resident or finished and the wait cannot deadlock.  Status and count
+// travel in ONE 64-bit word, so no ordering between separate words is needed.
+constexpr int kLookWMax = 8;
 template <int T>
-PSK_D int32_t lookback_exclusive_cta(unsigned long long* state, int32_t tile, int32_t count,
-                                     int32_t* s_sum /*[T/32]*/, int32_t* s_has /*[T/32]*/) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tile == 0) return 0;
-  int32_t excl = 0;
-  for (int32_t j = tile - 1;; j -= T) {
-    const int32_t idx = j - tid;
-    unsigned long long w = (unsigned long long)ST_PREFIX << 32;  // virtual prefix 0 before tile 0
-    if (idx >= 0) {
-      w = 0ull;
-      while ((w >> 32) == ST_INVALID) w = ld_volatile_u64(&state[idx]);
-    }
-    const unsigned pmask = __ballot_sync(0xffffffffu, (w >> 32) == ST_PREFIX);
-    const int first = pmask ? (__ffs((int)pmask) - 1) : 32;
-    int32_t c = (lane <= first) ? (int32_t)(uint32_t)w : 0;
+struct LookW {  // T * LookW<T>::value >= 1024 predecessors per round
+  static constexpr int value = T >= 256 ? 4 : 8;
+};
+
+struct LookWords {
+  unsigned long long w[kLookWMax];
+};
+
+template <int T>
+PSK_D LookWords lookback_issue(const unsigned long long* state, int32_t tile, int32_t D0) {
+  constexpr int kLookW = LookW<T>::value;
+  LookWords lw;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    __syncthreads();  // s_sum / s_has free (previous round or other users)
-    if (lane == 0) {
-      s_sum[warp] = c;
-      s_has[warp] = pmask != 0;
-    }
-    __syncthreads();
-    // every warp folds the warp results in tile order: lane q holds warp q's
-    const int32_t ws = (lane < T / 32) ? s_sum[lane] : 0;
-    const unsigned hmask = __ballot_sync(0xffffffffu, lane < T / 32 && s_has[lane] != 0);
-    const int fw = hmask ? (__ffs((int)hmask) - 1) : 32;
-    int32_t part = (lane <= fw) ? ws : 0;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-    excl += part;
-    if (hmask) break;
+  for (int u = 0; u < kLookW; ++u) {
+    const int32_t idx = tile - (D0 + 1 + (int32_t)threadIdx.x + T * u);
+    lw.w[u] = idx >= 0 ? ld_volatile_u64(&state[(long long)idx * kStateStride]) : 0ull;
   }
-  __syncthreads();
+  return lw;
+}
+
+template <int T>
+PSK_D int32_t lookback_finish(unsigned long long* state, int32_t tile, int32_t count, LookWords lw,
+                              int32_t* s_sum /*[LookW<T>::value * T/32]*/, int32_t* s_has /*[LookW<T>::value * T/32]*/) {
+  constexpr int NW = T / 32;
+  constexpr int kLookW = LookW<T>::value;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int32_t excl = 0;
+  if (tile > 0) {
+    for (int32_t D0 = 0;; D0 += T * kLookW) {
+      if (D0 > 0) lw = lookback_issue<T>(state, tile, D0);
+      __syncthreads();  // s_sum / s_has free (previous round or other users)
+#pragma unroll
+      for (int u = 0; u < kLookW; ++u) {
+        const int32_t idx = tile - (D0 + 1 + tid + T * u);
+        unsigned long long w = lw.w[u];
+        if (idx >= 0) {
+          while ((w >> 32) == ST_INVALID) {
+            sleep_ns(64);
+            w = ld_volatile_u64(&state[(long long)idx * kStateStride]);
+          }
+        }
+        // idx == -1: the virtual prefix 0 in front of tile 0
+        const bool is_prefix = idx >= 0 ? (w >> 32) == ST_PREFIX : idx == -1;
+        const unsigned pmask = __ballot_sync(0xffffffffu, is_prefix);
+        const int first = pmask ? (__ffs((int)pmask) - 1) : 32;
+        int32_t c = (lane <= first && idx >= 0) ? (int32_t)(uint32_t)w : 0;
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) c += __shfl_xor_sync(0xffffffffu, c, dd);
+        if (lane == 0) {
+          s_sum[u * NW + warp] = c;
+          s_has[u * NW + warp] = pmask != 0;
+        }
+      }
+      __syncthreads();
+      // fold in tile order (window, then warp): stop behind the first piece with a PREFIX
+      bool done = false;
+#pragma unroll
+      for (int q = 0; q < kLookW * NW; ++q) {
+        if (!done) {
+          excl += s_sum[q];
+          done = s_has[q] != 0;
+        }
+      }
+      if (done) break;
+    }
+  }
   if (tid == 0)
-    st_volatile_u64(&state[tile], ((unsigned long long)ST_PREFIX << 32) | (uint32_t)(excl + count));
+    st_volatile_u64(&state[(long long)tile * kStateStride],
+                    ((unsigned long long)ST_PREFIX << 32) | (uint32_t)(excl + count));
   return excl;
+}
+
+// both steps at once (callers without anything to overlap)
+template <int T>
+PSK_D int32_t lookback_exclusive_cta(unsigned long long* state, int32_t tile, int32_t count, int32_t* s_sum,
+                                     int32_t* s_has) {
+  return lookback_finish<T>(state, tile, count, lookback_issue<T>(state, tile, 0), s_sum, s_has);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -531,16 +584,21 @@ struct DescRegs {
   int2 la0, la1;
 };
 
-// one warp: take the next ticket and start fetching that tile's bounds (no barrier, and no
-// use of the loaded values: they stay in flight until store_tile_desc)
-PSK_D DescRegs fetch_tile_desc(DPlan* p, int k, int32_t n_tiles, bool views) {
+// one warp: start fetching the bounds of tile `ticket` (lane 0's value; no barrier, and no use
+// of the loaded values: they stay in flight until store_tile_desc).  The ticket itself is
+// taken earlier (take_ticket, at the top of the tile loop), so the atomic's round trip hides
+// behind the wait for the tile's runs and the cursor search.
+PSK_D int32_t take_ticket(DPlan* p) {
+  int32_t t = 0;
+  if ((threadIdx.x & 31) == 0) t = atomicAdd(&p->ctrl[CTRL_TICKET], 1);
+  return t;
+}
+PSK_D DescRegs fetch_tile_desc(DPlan* p, int k, int32_t n_tiles, bool views, int32_t ticket) {
   const int lane = threadIdx.x & 31;
   DescRegs r;
-  r.tile = 0;
   r.lo = r.hi = r.b0 = r.b1 = 0;
   r.la0 = r.la1 = make_int2(kSentinel, 0);
-  if (lane == 0) r.tile = atomicAdd(&p->ctrl[CTRL_TICKET], 1);
-  r.tile = __shfl_sync(0xffffffffu, r.tile, 0);
+  r.tile = __shfl_sync(0xffffffffu, ticket, 0);
   if (r.tile < n_tiles) {
     if (lane < k) {
       r.b0 = p->bounds[r.tile * k + lane];
@@ -631,8 +689,9 @@ PSK_D int flat_owner(const int32_t* flat, int k, int32_t f) {
 template <int K, bool TYPED_FLOAT, int VIEWS, typename Eval>
 PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
   constexpr int T = kTileThreads;
-  constexpr int RA = 0;            // region A: the bulk copies land here
-  constexpr int RB = kTileRegion;  // region B
+  constexpr int RA = 0;                // region A: the bulk copies land here
+  constexpr int RB = kTileRegion;      // regions B, C: kept spans of alternating tiles
+  constexpr int RC = 2 * kTileRegion;
 
   PSK_DYN_SMEM(smem_raw);
   const SmemPairs sm(smem_raw);
@@ -640,29 +699,73 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
   __shared__ TileDesc s_desc[2];
   __shared__ TileLayout s_layout[2];
   __shared__ int32_t s_warp[T / 32 + 2];
-  __shared__ int32_t s_lbhas[T / 32];
+  __shared__ int32_t s_lbsum[LookW<T>::value * (T / 32)];
+  __shared__ int32_t s_lbhas[LookW<T>::value * (T / 32)];
   __shared__ int32_t s_newstart[PSK_MAX_SOURCES];
   __shared__ psk_mbar_t s_bar;
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int k = p->k;
   constexpr bool typed_float = TYPED_FLOAT;
   const bool views = VIEWS < 0 ? (p->any_views != 0) : (VIEWS != 0);
   const int32_t span = p->span;
   const int32_t n_tiles = p->n_tiles;
-  // without views the merge reads region A and keeps its spans in B; with views the squeeze
-  // moves the mapped runs A -> B and the roles swap
+  // Without views the merge reads region A and keeps its spans in B (or C); they stay there
+  // while the CTA already works on the next tile -- until that tile has been searched (two
+  // regions) or merged (three regions) -- so the look-back of a tile is off the critical path.
+  // With views the squeeze moves the mapped runs A -> B, the merge keeps its spans in A and
+  // they are written out at once.
   const int RD = views ? RB : RA;
-  const int WR = views ? RA : RB;
 
   if (tid == 0) mbar_init(&s_bar, 1);
   __syncthreads();
   if (warp == 0) {
-    store_tile_desc(fetch_tile_desc(p, k, n_tiles, views), &s_desc[0], k);
+    const int32_t t0 = take_ticket(p);
+    store_tile_desc(fetch_tile_desc(p, k, n_tiles, views, t0), &s_desc[0], k);
     __syncwarp();
     if (s_desc[0].tile < n_tiles) issue_tile_copies(p, s_desc[0], k, sm, RA, &s_layout[0], &s_bar);
   }
   __syncthreads();
+
+  // spans of the previous tile that still wait for their place in the output
+  int32_t pend_tile = -1, pend_total = 0, pend_n = 0, pend_base = 0, pend_ofs = 0, pend_region = 0;
+  LookWords pend_look;
+#pragma unroll
+  for (int u = 0; u < kLookWMax; ++u) pend_look.w[u] = 0ull;
+
+  // global offset of a finished tile (decoupled look-back, its loads issued earlier), then
+  // every thread copies its own spans to their place in the output, 16 bytes per store
+  auto flush = [&](int32_t ftile, int32_t ftotal, int32_t fn, int32_t fbase, int32_t fofs, int fregion,
+                   const LookWords& look) {
+    const int32_t gofs = lookback_finish<T>(p->tile_state, ftile, ftotal, look, s_lbsum, s_lbhas);
+    if (tid == 0 && ftile == n_tiles - 1) {
+      const int32_t cnt = gofs + ftotal;
+      p->ctrl[CTRL_COUNT] = cnt;
+      *p->out_count = cnt;  // the count stays on the device too (queued consumers)
+      if (cnt <= p->out_capacity) {
+        p->out[cnt] = make_int2(kSentinel, 0);
+        p->out[cnt + 1] = make_int2(kSentinel, 0);
+      }
+    }
+    if (gofs + ftotal <= p->out_capacity) {
+      const int32_t o = gofs + fofs;
+      int2* const dst = p->out + o;
+      const int src = fregion + fbase;
+      int32_t j = 0;
+      if (fn > 0 && (o & 1)) {  // 16-byte alignment of the vector stores
+        dst[0] = sm.ld(src);
+        j = 1;
+      }
+      for (; j + 1 < fn; j += 2) {
+        const int2 a = sm.ld(src + j), b = sm.ld(src + j + 1);
+        *reinterpret_cast<uint4*>(dst + j) = make_uint4((unsigned)a.x, (unsigned)a.y, (unsigned)b.x, (unsigned)b.y);
+      }
+      if (j < fn) dst[j] = sm.ld(src + j);
+    } else if (tid == 0) {
+      p->ctrl[CTRL_ERROR] = 2;
+    }
+    __syncthreads();  // the span region may be overwritten now
+  };
 
   PSK_PHASE_DECL;
   for (int it = 0;; ++it) {
@@ -673,12 +776,13 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     const int32_t lo = d.lo, hi = d.hi;
     const bool fail = lay.ok == 0;
 
-    // ---- warp 0 starts fetching the bounds of the next tile; everybody waits for this tile's
-    //      runs to land -------------------------------------------------------------------
-    DescRegs fetched;
-    fetched.tile = 0;
-    if (warp == 0) fetched = fetch_tile_desc(p, k, n_tiles, views);
+    // ---- warp 0 takes the ticket of the next tile (the atomic's result is not needed before
+    //      the search is done); everybody waits for this tile's runs to land; the look-back
+    //      entries for the spans that are still parked are requested now and read later ------
+    int32_t ticket = 0;
+    if (warp == 0) ticket = take_ticket(p);
     mbar_wait(&s_bar, (uint32_t)(it & 1));
+    if (pend_tile >= 0) pend_look = lookback_issue<T>(p->tile_state, pend_tile, 0);
     PSK_PHASE(0);
 
     // ---- with views: map the raw ends through the view chains and squeeze out the runs
@@ -809,9 +913,21 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
       }
       cur_at[i] = sm.at(cur[i]);
     }
+    PSK_PHASE(2);
+    // the next tile's bounds: requested now, in flight during the merge
+    DescRegs fetched;
+    fetched.tile = 0;
+    if (warp == 0) fetched = fetch_tile_desc(p, k, n_tiles, views, ticket);
+
+    // ---- two regions: the previous tile's spans leave region B now ------------------------
+    if (kTileRegions == 2 && pend_tile >= 0) {
+      flush(pend_tile, pend_total, pend_n, pend_base, pend_ofs, pend_region, pend_look);
+      pend_tile = -1;
+    }
+    PSK_PHASE(5);
+    const int WR = views ? RA : ((kTileRegions == 3 && (it & 1)) ? RC : RB);
     const uint32_t out_begin = sm.at(WR + base);
     uint32_t out_at = out_begin;  // where this thread's next kept span goes
-    PSK_PHASE(2);
 
     // ---- sequential k-way merge over (c0, c1] -------------------------------------------
     // One distinct end is consumed per iteration: every source whose head run ends there
@@ -857,40 +973,30 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     PSK_PHASE(4);
     if (tid == 0) publish_aggregate(p->tile_state, tile, tile_total);
     const bool next_valid = s_desc[(it + 1) & 1].tile < n_tiles;
-    if (!views && warp == 0 && next_valid)
-      issue_tile_copies(p, s_desc[(it + 1) & 1], k, sm, RA, &s_layout[(it + 1) & 1], &s_bar);
-
-    // ---- global offset of the tile (decoupled look-back), then every warp writes the spans
-    //      of its own threads: lane regions are visited one after the other, 32 spans per
-    //      instruction, so the stores of a warp cover one contiguous piece of the output ----
-    const int32_t gofs = lookback_exclusive_cta<T>(p->tile_state, tile, tile_total, s_warp, s_lbhas);
-    PSK_PHASE(5);
-    if (tid == 0 && tile == n_tiles - 1) {
-      const int32_t cnt = gofs + tile_total;
-      p->ctrl[CTRL_COUNT] = cnt;
-      *p->out_count = cnt;  // the count stays on the device too (queued consumers)
-      if (cnt <= p->out_capacity) {
-        p->out[cnt] = make_int2(kSentinel, 0);
-        p->out[cnt + 1] = make_int2(kSentinel, 0);
-      }
+    if (!views) {
+      if (warp == 0 && next_valid)
+        issue_tile_copies(p, s_desc[(it + 1) & 1], k, sm, RA, &s_layout[(it + 1) & 1], &s_bar);
+      // three regions: the PREVIOUS tile's spans leave their region now
+      if (kTileRegions == 3 && pend_tile >= 0)
+        flush(pend_tile, pend_total, pend_n, pend_base, pend_ofs, pend_region, pend_look);
+      else
+        __syncthreads();  // the next tile's layout is visible to everybody
+      pend_tile = tile;
+      pend_total = tile_total;
+      pend_n = n;
+      pend_base = base;
+      pend_ofs = my_ofs;
+      pend_region = WR;
+    } else {
+      flush(tile, tile_total, n, base, my_ofs, WR, lookback_issue<T>(p->tile_state, tile, 0));
+      if (warp == 0 && next_valid)
+        issue_tile_copies(p, s_desc[(it + 1) & 1], k, sm, RA, &s_layout[(it + 1) & 1], &s_bar);
+      __syncthreads();
     }
-    if (gofs + tile_total <= p->out_capacity) {
-      int2* const dst = p->out + gofs;
-      for (int l = 0; l < 32; ++l) {
-        const int32_t n_l = __shfl_sync(0xffffffffu, n, l);
-        const int32_t b_l = __shfl_sync(0xffffffffu, base, l);
-        const int32_t o_l = __shfl_sync(0xffffffffu, my_ofs, l);
-        for (int32_t jj = lane; jj < n_l; jj += 32) dst[o_l + jj] = sm.ld(WR + b_l + jj);
-      }
-    } else if (tid == 0) {
-      p->ctrl[CTRL_ERROR] = 2;
-    }
-    __syncthreads();  // the span region may be overwritten now
-    if (views && warp == 0 && next_valid)
-      issue_tile_copies(p, s_desc[(it + 1) & 1], k, sm, RA, &s_layout[(it + 1) & 1], &s_bar);
-    if (views) __syncthreads();  // the layout of the next tile is visible to everybody
     PSK_PHASE(6);
   }
+  if (pend_tile >= 0)
+    flush(pend_tile, pend_total, pend_n, pend_base, pend_ofs, pend_region, lookback_issue<T>(p->tile_state, pend_tile, 0));
   PSK_PHASE_FLUSH;
 }
 

@@ -189,10 +189,10 @@ std::string gen_source(int K, bool typed_float, bool views, int nprog, const psk
   return src;
 }
 
-std::string cache_key(int K, bool typed_float, bool views, int T, int CAP, int nprog, const psk_node* prog) {
+std::string cache_key(int K, bool typed_float, bool views, int T, int CAP, int regions, int nprog, const psk_node* prog) {
   std::string key;
   key.reserve(nprog * 3 + 24);
-  key += std::to_string(T) + "/" + std::to_string(CAP) + "/";
+  key += std::to_string(T) + "/" + std::to_string(CAP) + "/" + std::to_string(regions) + "/";
   key += (char)K;
   key += typed_float ? 'T' : 'B';
   key += views ? 'V' : 'F';
@@ -203,7 +203,7 @@ std::string cache_key(int K, bool typed_float, bool views, int T, int CAP, int n
   return key;
 }
 
-bool compile_cubin(int K, bool typed_float, bool views, int T, int CAP, int nprog, const psk_node* prog,
+bool compile_cubin(int K, bool typed_float, bool views, int T, int CAP, int regions, int nprog, const psk_node* prog,
                    std::vector<char>* cubin, std::string* why) {
   const std::string src = gen_source(K, typed_float, views, nprog, prog);
   nvrtcProgram np = nullptr;
@@ -215,11 +215,12 @@ bool compile_cubin(int K, bool typed_float, bool views, int T, int CAP, int npro
   }
   const std::string opt_t = "-DPSK_TILE_THREADS=" + std::to_string(T);
   const std::string opt_c = "-DPSK_TILE_CAP=" + std::to_string(CAP);
+  const std::string opt_r = "-DPSK_TILE_REGIONS=" + std::to_string(regions);
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo",
 #ifdef PSK_PHASE_TIMING
                         "-DPSK_PHASE_TIMING",
 #endif
-                        opt_t.c_str(), opt_c.c_str(),
+                        opt_t.c_str(), opt_c.c_str(), opt_r.c_str(),
   };
   r = g_api.nvrtcCompileProgram(np, (int)(sizeof(opts) / sizeof(opts[0])), opts);
   if (r != 0) {
@@ -251,10 +252,10 @@ bool compile_cubin(int K, bool typed_float, bool views, int T, int CAP, int npro
   return true;
 }
 
-JitKernel* compile(int K, bool typed_float, bool views, int T, int CAP, int nprog, const psk_node* prog,
+JitKernel* compile(int K, bool typed_float, bool views, int T, int CAP, int regions, int nprog, const psk_node* prog,
                    std::string* why) {
   std::vector<char> cubin;
-  if (!compile_cubin(K, typed_float, views, T, CAP, nprog, prog, &cubin, why)) return nullptr;
+  if (!compile_cubin(K, typed_float, views, T, CAP, regions, nprog, prog, &cubin, why)) return nullptr;
   void* mod = nullptr;
   int r = g_api.cuModuleLoadData(&mod, cubin.data());
   if (r != 0) {
@@ -274,7 +275,7 @@ JitKernel* compile(int K, bool typed_float, bool views, int T, int CAP, int npro
 
 }  // namespace
 
-const JitKernel* jit_get_merge_eval(int K, bool typed_float, bool views, int T, int CAP, int nprog,
+const JitKernel* jit_get_merge_eval(int K, bool typed_float, bool views, int T, int CAP, int regions, int nprog,
                                     const psk_node* prog, const char** why) {
   std::lock_guard<std::mutex> l(g_mu);
   static std::string s_why;
@@ -282,13 +283,13 @@ const JitKernel* jit_get_merge_eval(int K, bool typed_float, bool views, int T, 
     if (why) *why = g_api.why.c_str();
     return nullptr;
   }
-  const std::string key = cache_key(K, typed_float, views, T, CAP, nprog, prog);
+  const std::string key = cache_key(K, typed_float, views, T, CAP, regions, nprog, prog);
   auto it = g_cache.find(key);
   if (it != g_cache.end()) {
     if (!it->second && why) *why = "previous compilation of this program failed";
     return it->second;
   }
-  JitKernel* k = compile(K, typed_float, views, T, CAP, nprog, prog, &s_why);
+  JitKernel* k = compile(K, typed_float, views, T, CAP, regions, nprog, prog, &s_why);
   if (k) {
     ++g_compiled;
   } else {
@@ -315,12 +316,12 @@ int jit_launch(const JitKernel* k, unsigned grid, unsigned block, size_t smem, v
   return g_api.cuLaunchKernel(k->function, grid, 1, 1, block, 1, 1, (unsigned)smem, stream, args, nullptr);
 }
 
-int jit_compile_check(int K, bool typed_float, int T, int CAP, int nprog, const psk_node* prog, char* log, int loglen) {
+int jit_compile_check(int K, bool typed_float, int T, int CAP, int regions, int nprog, const psk_node* prog, char* log, int loglen) {
   std::lock_guard<std::mutex> l(g_mu);
   std::string why;
   std::vector<char> cubin;
-  bool ok = load_nvrtc() && compile_cubin(K, typed_float, false, T, CAP, nprog, prog, &cubin, &why) &&
-            compile_cubin(K, typed_float, true, T, CAP, nprog, prog, &cubin, &why);  // both staging variants
+  bool ok = load_nvrtc() && compile_cubin(K, typed_float, false, T, CAP, regions, nprog, prog, &cubin, &why) &&
+            compile_cubin(K, typed_float, true, T, CAP, regions, nprog, prog, &cubin, &why);  // both staging variants
   if (!ok && why.empty()) why = g_api.why;
   if (log && loglen > 0) {
     std::string msg = ok ? ("ok cubin bytes=" + std::to_string(cubin.size())) : why;

@@ -27,7 +27,7 @@ struct JitKernel {
 // Returns nullptr when JIT is unavailable/disabled or compilation failed (the reason is
 // appended to *why when given).
 // T / CAP: threads per CTA and runs per tile the kernel is compiled for (-DPSK_TILE_THREADS / -DPSK_TILE_CAP).
-const JitKernel* jit_get_merge_eval(int K, bool typed_float, bool views, int T, int CAP, int nprog, const psk_node* prog,
+const JitKernel* jit_get_merge_eval(int K, bool typed_float, bool views, int T, int CAP, int regions, int nprog, const psk_node* prog,
                                     const char** why);
 
 // cuLaunchKernel on `stream`; returns 0 on success.
@@ -35,7 +35,7 @@ int jit_launch(const JitKernel* k, unsigned grid, unsigned block, size_t smem, v
 
 // NVRTC stage only (no driver needed): 0 when the specialised source compiles to an sm_100a
 // cubin.  Used by the CPU-side tests.
-int jit_compile_check(int K, bool typed_float, int T, int CAP, int nprog, const psk_node* prog, char* log, int loglen);
+int jit_compile_check(int K, bool typed_float, int T, int CAP, int regions, int nprog, const psk_node* prog, char* log, int loglen);
 
 // number of modules compiled so far (diagnostics / tests)
 int jit_compiled_count();

@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 
+#include "psk_conv.cuh"
 #include "psk_convert.cuh"
 #include "psk_eval.cuh"
 #ifndef PSK_CPU_SIM
@@ -61,7 +62,7 @@ struct Ctx {
   bool convert_vec = false;        // dense <-> RLE with 16-byte accesses (psk_set_vector_conversion)
   int64_t small_partition = 2048;  // samples up to which one block does the whole partition
   int stagger_ns = 0;
-  int jit_T = kTileThreads, jit_CAP = kTileCap;  // tile geometry of the specialised kernels (PSKB200_TILE_*)
+  int jit_T = kTileThreads, jit_CAP = kTileCap, jit_regions = kTileRegions;  // tile geometry of the specialised kernels (PSKB200_TILE_*)
   cudaEvent_t xev = nullptr;                     // orders the download stream behind the library stream
   unsigned long long* trace_buf = nullptr;  // PSK_PHASE_TIMING builds: device trace buffer
   int64_t trace_cap = 0, trace_tiles = 0;
@@ -168,6 +169,10 @@ psk_status do_init(int device) {
     const int t = atoi(sv);
     if (t >= 32 && t <= 1024 && t % 32 == 0) g.jit_T = t;
   }
+  if (const char* sv = getenv("PSKB200_TILE_REGIONS")) {
+    const int r = atoi(sv);
+    if (r == 2 || r == 3) g.jit_regions = r;
+  }
   if (const char* sv = getenv("PSKB200_TILE_CAP")) {
     const int c = atoi(sv);
     if (c >= 512 && c <= 13000 && c % 64 == 0) g.jit_CAP = c;
@@ -220,6 +225,27 @@ psk_status new_store(int dtype, int64_t capacity, psk_store_t* out) {
 // event lives until the store is released)
 void wait_ready(psk_store_s* s) {
   if (s->ready) cudaStreamWaitEvent(g.stream, s->ready, 0);
+}
+
+// Shrink a result whose worst-case allocation is much larger than what it holds (the count is
+// known on the host here): copy into an exact-size allocation, free the big one.  Both are
+// stream-ordered, so kernels already queued on the old pointer are unaffected.
+void right_size(psk_store_s* s) {
+  if (s->nruns <= 0 || s->capacity < 4096 || s->capacity <= 2 * s->nruns) return;
+  int2* small = nullptr;
+  if (cudaMallocAsync(reinterpret_cast<void**>(&small), (size_t)(s->nruns + kStorePad) * 8, g.stream) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  // runs + the two sentinel pairs; the count word moves to the new padding
+  cudaMemcpyAsync(small, s->d_runs, (size_t)(s->nruns + 2) * 8, cudaMemcpyDeviceToDevice, g.stream);
+  int32_t* new_count = reinterpret_cast<int32_t*>(small + s->nruns + kStorePad - 1);
+  cudaMemcpyAsync(new_count, s->d_count, 4, cudaMemcpyDeviceToDevice, g.stream);
+  cudaFreeAsync(s->d_runs, g.stream);
+  g.live_bytes -= (s->capacity - s->nruns) * 8;
+  s->d_runs = small;
+  s->d_count = new_count;
+  s->capacity = s->nruns;
 }
 
 // ---- view descriptors ----------------------------------------------------------------
@@ -425,6 +451,16 @@ psk_status encode_device(const void* d_dense, int64_t n, psk_store_t* out) {
 }
 }  // namespace
 
+namespace {
+template <int KW, int KH, int KD>
+void launch_conv(bool is_f, unsigned grid, const ConvParams& cp) {
+  auto kf = k_conv_rows<KW, KH, KD, true>;
+  auto ki = k_conv_rows<KW, KH, KD, false>;
+  if (is_f) LAUNCH(kf, grid, kConvRowThreads, 0, cp);
+  else LAUNCH(ki, grid, kConvRowThreads, 0, cp);
+}
+}  // namespace
+
 // ========================================================================================
 extern "C" {
 
@@ -560,12 +596,15 @@ psk_status psk_set_jit_threshold(int64_t min_total_runs) {
 
 int64_t psk_jit_launch_count(void) { return g.jit_launches; }
 
-psk_status psk_set_tile_geometry(int32_t threads, int32_t cap) {
+psk_status psk_set_tile_geometry(int32_t threads, int32_t cap, int32_t regions) {
   std::lock_guard<std::recursive_mutex> api_lock_(g.api_mu);
   PSK_CHECK_ARG(threads >= 32 && threads <= 1024 && threads % 32 == 0);
   PSK_CHECK_ARG(cap >= 512 && cap <= 13000 && cap % 64 == 0);
+  PSK_CHECK_ARG(regions == 2 || regions == 3);
+  PSK_CHECK_ARG((size_t)regions * (size_t)(cap + kTileSlack) * 8u + 6144 <= 227 * 1024);
   g.jit_T = threads;
   g.jit_CAP = cap;
+  g.jit_regions = regions;
   return PSK_OK;
 }
 
@@ -575,7 +614,7 @@ int32_t psk_jit_compile_check(int32_t k, int32_t nprog, const psk_node* prog, ch
   return -1;
 #else
   if (validate_program(k, nprog, prog) != PSK_OK) return 2;
-  return jit_compile_check(k, false, g.jit_T, g.jit_CAP, nprog, prog, log, loglen);
+  return jit_compile_check(k, false, g.jit_T, g.jit_CAP, g.jit_regions, nprog, prog, log, loglen);
 #endif
 }
 
@@ -1019,20 +1058,21 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
   hp.on_device = on_device ? 1 : 0;
 
   // ---- which kernel: the specialised one (NVRTC) for large evaluations ---------------------
-  int T = kTileThreads, CAP = kTileCap;
+  int T = kTileThreads, CAP = kTileCap, regions = kTileRegions;
 #ifndef PSK_CPU_SIM
   const JitKernel* jk = nullptr;
   if (total_runs >= g.jit_min_runs) {
     // K = k exactly: no padding sources in the specialised kernel
-    jk = jit_get_merge_eval(k, hp.eq != 0, any_views, g.jit_T, g.jit_CAP, nprog, prog, nullptr);
+    jk = jit_get_merge_eval(k, hp.eq != 0, any_views, g.jit_T, g.jit_CAP, g.jit_regions, nprog, prog, nullptr);
     if (jk) {
       T = g.jit_T;
       CAP = g.jit_CAP;
+      regions = g.jit_regions;
     }
   }
 #endif
-  const size_t smem = 2u * (size_t)(CAP + kTileSlack) * 8u;
-  int ctas = (int)((227 * 1024) / (smem + 5120));
+  const size_t smem = (size_t)regions * (size_t)(CAP + kTileSlack) * 8u;
+  int ctas = (int)((227 * 1024) / (smem + 6144));
   if (ctas > 2048 / T) ctas = 2048 / T;
   if (ctas < 1) ctas = 1;
 
@@ -1070,7 +1110,7 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
 
   // ---- scratch: [tile_state | phase | ctrl | bounds | tile_hi | lookahead | plan] ------------
   size_t o_state = 0;
-  size_t o_phase = o_state + (size_t)max_tiles * 8;
+  size_t o_phase = o_state + (size_t)max_tiles * 8 * kStateStride;
   size_t o_ctrl = o_phase + 8 * 8;
   size_t o_bounds = o_ctrl + CTRL_WORDS * 4;
   size_t o_hi = o_bounds + (size_t)(max_tiles + 1) * k * 4;
@@ -1191,6 +1231,7 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
     psk_store_release(res);
     return fail(PSK_ESTATE, "psk_eval: produced no runs");
   }
+  right_size(res);
   *out = res;
   return PSK_OK;
 }
@@ -1206,6 +1247,110 @@ psk_status psk_eval_async(int32_t k, const psk_source* sources, int32_t nprog, c
                           psk_dtype out_dtype, psk_eq eq, psk_store_t* out) {
   NEED_INIT();
   return eval_impl(k, sources, nprog, prog, out_dtype, eq, true, out);
+}
+
+
+// ---- stencil over runs: conv_2d / conv_3d (src/pyskip/convolve.py:5-59) ------------------
+namespace {
+
+
+}  // namespace
+
+int32_t psk_conv_supported(int32_t ndim, const int32_t* kshape) {
+  if (!kshape) return 0;
+  if (ndim == 3) return kshape[0] == 3 && kshape[1] == 3 && kshape[2] == 3;
+  if (ndim == 2) return kshape[0] == 3 && kshape[1] == 3;
+  return 0;
+}
+
+psk_status psk_conv_nd(psk_store_t s, int32_t ndim, const int32_t* shape, const int32_t* kshape,
+                       const uint32_t* weights, const int32_t* pad, uint32_t fill_bits, psk_eq eq,
+                       psk_store_t* out) {
+  NEED_INIT();
+  PSK_CHECK_ARG(s != nullptr && out != nullptr && shape && kshape && weights && pad);
+  PSK_CHECK_ARG(ndim == 2 || ndim == 3);
+  if (!psk_conv_supported(ndim, kshape))
+    return fail(PSK_EINVAL, "psk_conv_nd: kernel shape not supported by the stencil kernel (3x3, 3x3x3)");
+  PSK_CHECK_ARG(s->dtype == PSK_I32 || s->dtype == PSK_F32);  // arithmetic types (type_binds.hpp:174-236)
+  if (s->failed) READY(s);
+  const bool queued = s->pending_slot >= 0;
+  if (!queued) wait_ready(s);
+  ConvParams cp;
+  memset(&cp, 0, sizeof(cp));
+  int64_t n_in = 1, n_out = 1;
+  int32_t ext[3] = {1, 1, 1}, pd[3] = {0, 0, 0}, ks[3] = {1, 1, 1}, oext[3] = {1, 1, 1};
+  for (int i = 0; i < ndim; ++i) {
+    PSK_CHECK_ARG(shape[i] > 0 && pad[i] >= 0);
+    ext[i] = shape[i];
+    pd[i] = pad[i];
+    ks[i] = kshape[i];
+    oext[i] = shape[i] + 2 * pad[i] - kshape[i] + 1;
+    PSK_CHECK_ARG(oext[i] > 0);
+    n_in *= ext[i];
+    n_out *= oext[i];
+  }
+  PSK_CHECK_ARG(n_in == s->span);
+  PSK_CHECK_ARG(n_in <= 0x7fffffffLL && n_out <= 0x7fffffffLL);
+  // the padded tensor of the reference must be representable too (TensorShape::len, tensor.hpp:38-44)
+  PSK_CHECK_ARG((int64_t)(ext[0] + 2 * pd[0]) * (ext[1] + 2 * pd[1]) * (ext[2] + 2 * pd[2]) <= 0x7fffffffLL);
+  const int taps = ks[0] * ks[1] * ks[2];
+  cp.runs = s->d_runs;
+  cp.d_count = queued ? s->d_count : nullptr;
+  cp.nruns = (int32_t)(queued ? s->capacity : s->nruns);
+  cp.W = ext[0]; cp.H = ext[1]; cp.D = ext[2];
+  cp.px = pd[0]; cp.py = pd[1]; cp.pz = pd[2];
+  cp.OW = oext[0]; cp.OH = oext[1]; cp.OD = oext[2];
+  cp.fill = fill_bits;
+  cp.typed_float = (eq == PSK_EQ_TYPED && s->dtype == PSK_F32) ? 1 : 0;
+  for (int t = 0; t < taps; ++t) cp.w[t] = weights[t];
+  // every output row sees, per tap, the pieces of one input row: its runs + two padding pieces
+  const int64_t in_rows = (int64_t)ext[1] * ext[2];
+  const int64_t out_rows = (int64_t)oext[1] * oext[2];
+  int64_t cap = (int64_t)taps * ((int64_t)cp.nruns + 3 * in_rows) + 2 * out_rows;
+  if (cap > n_out) cap = n_out;
+  const int64_t n_tiles = (out_rows + kConvRowThreads - 1) / kConvRowThreads;
+  // scratch: [tile_state | ctrl | row_start]
+  const size_t o_ctrl = (size_t)n_tiles * 8 * kStateStride;
+  const size_t o_rows = o_ctrl + 16 * 4;
+  unsigned char* scratch = nullptr;
+  psk_status st = dmalloc(reinterpret_cast<void**>(&scratch), o_rows + (size_t)in_rows * 4);
+  if (st != PSK_OK) return st;
+  psk_store_t res = nullptr;
+  st = new_store(s->dtype, cap, &res);
+  if (st != PSK_OK) {
+    cudaFreeAsync(scratch, g.stream);
+    return st;
+  }
+  cp.tile_state = reinterpret_cast<unsigned long long*>(scratch);
+  cp.ctrl = reinterpret_cast<int32_t*>(scratch + o_ctrl);
+  cp.row_start = reinterpret_cast<int32_t*>(scratch + o_rows);
+  cp.out = res->d_runs;
+  cp.out_capacity = (int32_t)cap;
+  cp.out_count = res->d_count;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, o_rows, g.stream);
+  if (e == cudaSuccess) {
+    LAUNCH(k_conv_row_starts, (unsigned)((in_rows + 255) / 256), 256, 0, cp);
+    const bool is_f = s->dtype == PSK_F32;
+    if (ndim == 3) launch_conv<3, 3, 3>(is_f, (unsigned)n_tiles, cp);
+    else launch_conv<3, 3, 1>(is_f, (unsigned)n_tiles, cp);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(g.h_ctrl, cp.ctrl, CTRL_WORDS * 4, cudaMemcpyDeviceToHost, g.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+  cudaFreeAsync(scratch, g.stream);
+  if (e != cudaSuccess) {
+    psk_store_release(res);
+    return fail(PSK_ECUDA, std::string("psk_conv_nd: ") + cudaGetErrorString(e));
+  }
+  if (g.h_ctrl[CTRL_ERROR] != 0) {
+    psk_store_release(res);
+    return fail(PSK_ESTATE, "psk_conv_nd: output capacity exceeded (internal bound violated)");
+  }
+  res->nruns = g.h_ctrl[CTRL_COUNT];
+  res->span = (int32_t)n_out;
+  right_size(res);
+  *out = res;
+  return PSK_OK;
 }
 
 // ---- masks -----------------------------------------------------------------------------

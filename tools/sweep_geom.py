@@ -32,8 +32,9 @@ def main():
     prog = bench.dag_program(A)
     expect = None
     for geom in args.geoms.split(","):
-        T, CAP = (int(x) for x in geom.split("x"))
-        lib.set_tile_geometry(T, CAP)
+        f = [int(x) for x in geom.split("x")]
+        T, CAP, R = f[0], f[1], (f[2] if len(f) > 2 else 2)
+        lib.set_tile_geometry(T, CAP, R)
         r = lib.eval(srcs, prog, A.F32, A.EQ_BITWISE)  # compiles
         n = r.nruns
         if expect is None:
@@ -47,7 +48,7 @@ def main():
         ms = lib.timer_stop() / args.reps
         kms, nev, rin, rout = lib.profile_read()
         lib.profile(False)
-        print(json.dumps({"T": T, "CAP": CAP, "kernel_ms": kms / max(1, nev), "step_ms": ms, "runs_out": n,
+        print(json.dumps({"T": T, "CAP": CAP, "R": R, "kernel_ms": kms / max(1, nev), "step_ms": ms, "runs_out": n,
                           "ok": n == expect, "GBps": 8.0 * (4 * n_runs + n) / (kms / max(1, nev) * 1e-3) / 1e9}))
         sys.stdout.flush()
 
