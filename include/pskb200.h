@@ -185,11 +185,11 @@ PSK_API psk_status psk_set_vector_conversion(int32_t enable);
 PSK_API int32_t psk_jit_compile_check(int32_t k, int32_t nprog, const psk_node* prog, char* log,
                                       int32_t loglen);
 /* Tuning aid: tile geometry of the specialised kernels -- threads per CTA (multiple of 32),
- * runs per tile (multiple of 64) and shared-memory regions (2: a tile's spans are written out
- * while the next tile is being prepared; 3: one tile later).  The partition and the number of
- * resident CTAs follow.  Results do not depend on it.  Also read once from
- * PSKB200_TILE_THREADS / PSKB200_TILE_CAP / PSKB200_TILE_REGIONS. */
-PSK_API psk_status psk_set_tile_geometry(int32_t threads, int32_t cap, int32_t regions);
+ * runs per tile (multiple of 64) and park depth (finished tiles a CTA may hold back in its
+ * global-memory ring while tiles in front of them are still being merged, 1..16).  The
+ * partition and the number of resident CTAs follow.  Results do not depend on it.  Also read
+ * once from PSKB200_TILE_THREADS / PSKB200_TILE_CAP / PSKB200_PARK_DEPTH. */
+PSK_API psk_status psk_set_tile_geometry(int32_t threads, int32_t cap, int32_t park_depth);
 /* How many psk_eval calls ran on a specialised kernel. */
 PSK_API int64_t psk_jit_launch_count(void);
 /* Measurement aid for bench.py's roofline line: when enabled, psk_eval brackets its
@@ -217,6 +217,17 @@ PSK_API psk_status psk_copy_synchronize(void);
 PSK_API psk_status psk_store_from_device_runs(psk_dtype dtype, int64_t nruns,
                                               const int32_t* d_ends, const uint32_t* d_vals,
                                               psk_store_t* out);
+/* Runs in the store's own pair layout, device to device on the library stream: export into a
+ * caller-owned device buffer of nruns pairs (an NCCL send buffer), and a store from nruns
+ * validated pairs in device memory (a receive buffer).  The multi-GPU halo exchange moves
+ * runs this way: exact sizes, no host copy. */
+PSK_API psk_status psk_store_export_pairs(psk_store_t s, void* d_pairs);
+PSK_API psk_status psk_store_from_device_pairs(psk_dtype dtype, int64_t nruns, const void* d_pairs,
+                                               psk_store_t* out);
+/* parts[0] ++ parts[1] ++ ... (spans add up; the result need not be canonical at the seams,
+ * which the evaluation path does not require: SURVEY.md A.1).  Used to put halo slices
+ * around a z-slab. */
+PSK_API psk_status psk_store_concat(int32_t n, const psk_store_t* parts, psk_store_t* out);
 /* core::make_store(span, fill) (core.hpp:104-111): one run. */
 PSK_API psk_status psk_store_fill(psk_dtype dtype, int32_t span, uint32_t fill_bits,
                                   psk_store_t* out);
@@ -233,6 +244,10 @@ PSK_API psk_status psk_store_to_dense_device(psk_store_t s, void* d_out);
 PSK_API psk_status psk_store_runs(psk_store_t s, int32_t* ends, void* vals);
 PSK_API int64_t psk_store_nruns(psk_store_t s);
 PSK_API int32_t psk_store_span(psk_store_t s);
+/* 1 while the store is a queued result (psk_eval_async) whose run count has not reached the
+ * host yet: psk_store_nruns would wait for it; psk_eval / psk_reduce / psk_conv_nd /
+ * psk_store_boundary_device take it as an input WITHOUT waiting (the count is read on the device). */
+PSK_API int32_t psk_store_pending(psk_store_t s);
 PSK_API int32_t psk_store_dtype(psk_store_t s);
 /* Device pointer of the run array (valid while the store is alive): nruns pairs of
  * { int32 end; uint32 payload }, followed by two sentinel pairs (end = INT32_MAX). */
@@ -290,6 +305,14 @@ PSK_API psk_status psk_mask_nd(int32_t ndim, const int32_t* shape, const int32_t
  * fp64 and returns the fp64 bits; MAX/MIN over run values; PROD = prod(val^len) (int32
  * wrap / fp64). */
 PSK_API psk_status psk_reduce(psk_store_t s, psk_reduce_op op, uint64_t* result_bits);
+
+/* Segmented reduction: out[j] = reduction of the flat coordinates [j*seg_len, (j+1)*seg_len)
+ * -- reduce(op, t, axis=0) of src/pyskip/reduce.py:8-33 for a tensor whose fastest extent (or
+ * product of inner extents) is seg_len; span % seg_len == 0.  One pass over the runs; same
+ * arithmetic as psk_reduce (float32 results are the fp64 accumulation rounded once).  The
+ * result is a store of span/seg_len elements of the input's dtype (I32 / F32). */
+PSK_API psk_status psk_reduce_segments(psk_store_t s, int32_t seg_len, psk_reduce_op op,
+                                       psk_store_t* out);
 
 /* ---- multi-GPU helpers (fuse_stores boundary rule, detail/eval.hpp:568-607) ----------
  * A shard's first/last payloads and run count, for the stitch all-gather. */

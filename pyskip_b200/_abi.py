@@ -107,10 +107,15 @@ _SYMBOLS = [
     "psk_live_bytes", "psk_profile", "psk_profile_read", "psk_set_jit_threshold", "psk_set_tile_geometry", "psk_set_small_partition", "psk_set_vector_conversion", "psk_jit_launch_count", "psk_jit_compile_check", "psk_store_from_runs", "psk_store_from_runs_async", "psk_store_runs_async", "psk_copy_synchronize", "psk_store_from_device_runs", "psk_store_fill",
     "psk_store_from_dense", "psk_store_from_dense_device", "psk_store_to_dense",
     "psk_store_to_dense_device", "psk_store_runs", "psk_store_nruns", "psk_store_span",
-    "psk_store_dtype", "psk_store_device_pairs", "psk_store_first_value", "psk_eval_async", "psk_store_retain",
+    "psk_store_dtype", "psk_store_pending", "psk_store_export_pairs", "psk_store_from_device_pairs", "psk_store_concat", "psk_reduce_segments", "psk_conv_nd", "psk_conv_supported", "psk_store_device_pairs", "psk_store_first_value", "psk_eval_async", "psk_store_retain",
     "psk_store_release", "psk_eval", "psk_view_span", "psk_mask_nd", "psk_reduce",
     "psk_store_boundary", "psk_store_boundary_device", "psk_store_slice",
 ]
+
+
+def _h(s):
+    """psk_store_t of a Store wrapper or a raw handle (int)."""
+    return s.h if isinstance(s, Store) else int(s)
 
 
 class Store:
@@ -213,6 +218,15 @@ class Lib:
         c.psk_view_span.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         c.psk_mask_nd.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         c.psk_reduce.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        c.psk_reduce_segments.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.c_void_p]
+        c.psk_store_export_pairs.argtypes = [C.c_void_p, C.c_void_p]
+        c.psk_store_from_device_pairs.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+        c.psk_store_concat.argtypes = [C.c_int32, C.c_void_p, C.c_void_p]
+        c.psk_conv_nd.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                  C.c_int, C.c_void_p]
+        c.psk_conv_supported.argtypes = [C.c_int32, C.c_void_p]
+        c.psk_store_pending.argtypes = [C.c_void_p]
+        c.psk_set_tile_geometry.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         c.psk_init.argtypes = [C.c_int32]
         c.psk_timer_stop.argtypes = [C.c_void_p]
         c.psk_get_stream.argtypes = [C.c_void_p]
@@ -260,7 +274,7 @@ class Lib:
     def set_jit_threshold(self, min_total_runs: int):
         self._chk(self.c.psk_set_jit_threshold(C.c_int64(min_total_runs)))
 
-    def set_tile_geometry(self, threads: int, cap: int, regions: int = 2):
+    def set_tile_geometry(self, threads: int, cap: int, regions: int = 4):
         self._chk(self.c.psk_set_tile_geometry(C.c_int32(threads), C.c_int32(cap), C.c_int32(regions)))
 
     def set_vector_conversion(self, enable: bool):
@@ -321,6 +335,30 @@ class Lib:
         h = C.c_void_p()
         self._chk(self.c.psk_store_from_device_runs(dtype, nruns, C.c_void_p(d_ends), C.c_void_p(d_vals),
                                                     C.byref(h)))
+        return Store(self, h.value)
+
+    def store_export_pairs(self, s, d_ptr: int):
+        """Copy the store's nruns (end, payload) int32 pairs into device memory at d_ptr."""
+        self._chk(self.c.psk_store_export_pairs(C.c_void_p(_h(s)), C.c_void_p(d_ptr)))
+
+    def store_from_device_pairs(self, dtype: int, nruns: int, d_ptr: int) -> Store:
+        h = C.c_void_p()
+        self._chk(self.c.psk_store_from_device_pairs(dtype, C.c_int64(nruns), C.c_void_p(d_ptr), C.byref(h)))
+        return Store(self, h.value)
+
+    def store_concat(self, parts) -> Store:
+        arr = (C.c_void_p * len(parts))(*[_h(p) for p in parts])
+        h = C.c_void_p()
+        self._chk(self.c.psk_store_concat(len(parts), arr, C.byref(h)))
+        return Store(self, h.value)
+
+    def conv_nd(self, s, shape, kshape, weights, pads, fill_bits: int, eq: int = EQ_BITWISE) -> Store:
+        nd = len(shape)
+        I = C.c_int32 * nd
+        w = np.ascontiguousarray(weights).view(np.uint32).ravel()
+        h = C.c_void_p()
+        self._chk(self.c.psk_conv_nd(C.c_void_p(_h(s)), nd, I(*shape), I(*kshape), w.ctypes.data_as(C.c_void_p),
+                                     I(*pads), C.c_uint32(fill_bits), eq, C.byref(h)))
         return Store(self, h.value)
 
     def store_fill(self, dtype: int, span: int, value) -> Store:

@@ -40,6 +40,8 @@ struct Backend {
   PSK_FN(psk_conv_supported)
   PSK_FN(psk_conv_nd)
   PSK_FN(psk_eval_async)
+  PSK_FN(psk_store_pending)
+  PSK_FN(psk_reduce_segments)
 #undef PSK_FN
 };
 
@@ -84,6 +86,8 @@ inline void bind_backend(const std::string& path, bool rebind) {
   PSK_FN(psk_conv_supported)
   PSK_FN(psk_conv_nd)
   PSK_FN(psk_eval_async)
+  PSK_FN(psk_store_pending)
+  PSK_FN(psk_reduce_segments)
 #undef PSK_FN
   b = nb;
 }

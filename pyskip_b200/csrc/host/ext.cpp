@@ -194,6 +194,28 @@ void bind_array(py::module& m, const char* name) {
     }
     return to_py_scalar<DT>(Array::value_of(DT, (uint32_t)bits));
   });
+  // out[j] = reduction of the flat coordinates [j * seg_len, (j + 1) * seg_len)  (psk_reduce_segments)
+  if (DT == PSK_I32 || DT == PSK_F32) {
+    cls.def("_reduce_segments", [](const A& s, int op, int32_t seg_len) {
+      PSK_CHECK_ARGUMENT(!s.a.empty());
+      StoreRef st = s.a.store();
+      psk_store_t h = nullptr;
+      check(backend().psk_reduce_segments(st.get(), seg_len, (psk_reduce_op)op, &h));
+      return wrap<DT>(Array::from_store(StoreRef(h)));
+    });
+  }
+  // interop with the ctypes binding of the same library (pyskip_b200._abi): the psk_store_t of
+  // the materialised array (retained for the caller, who releases it), and an array that
+  // adopts a handle (takes over the caller's reference)
+  cls.def("_store_handle", [](const A& s) {
+    PSK_CHECK_ARGUMENT(!s.a.empty());
+    StoreRef st = s.a.eval().store();
+    backend().psk_store_retain(st.get());
+    return (uintptr_t)st.get();
+  });
+  cls.def_static("_adopt_store", [](uintptr_t handle) {
+    return wrap<DT>(Array::from_store(StoreRef(reinterpret_cast<psk_store_t>(handle))));
+  });
   cls.def_static("_from_runs", [](py::array_t<int32_t, py::array::c_style | py::array::forcecast> ends,
                                   py::array_t<T, py::array::c_style | py::array::forcecast> vals) {
     PSK_CHECK_ARGUMENT(ends.size() == vals.size());

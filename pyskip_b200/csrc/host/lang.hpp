@@ -214,7 +214,8 @@ class Planner {
 
   void replace_with_store(const Expr* e, StoreRef st) {
     ExprPtr s = make_store_expr(st, resolve(e)->dtype);
-    if (st.nruns() == 1) {
+    // (a queued result is not waited for just to learn whether it is a constant)
+    if (!backend().psk_store_pending(st.get()) && st.nruns() == 1) {
       uint32_t bits = 0;
       check(backend().psk_store_first_value(st.get(), &bits));
       s->is_const = true;
@@ -261,11 +262,13 @@ class Planner {
     }
   }
 
-  StoreRef run_sub(const Expr* e) { return run_node(e, PSK_EQ_BITWISE); }
+  // intermediates are queued (psk_eval_async): their consumers read the run count on the device,
+  // so a cut expression costs one host round trip in total, not one per step
+  StoreRef run_sub(const Expr* e) { return run_node(e, PSK_EQ_BITWISE, /*queued=*/true); }
 
   StoreRef run(const ExprPtr& root, psk_eq eq, bool) {
     make_feasible(root.get());
-    return run_node(root.get(), eq);
+    return run_node(root.get(), eq, /*queued=*/false);
   }
 
   void lower(const Expr* e0, ViewChain chain, Step& st) {
@@ -327,7 +330,7 @@ class Planner {
     return true;
   }
 
-  StoreRef run_node(const Expr* e0, psk_eq eq) {
+  StoreRef run_node(const Expr* e0, psk_eq eq, bool queued) {
     const Expr* e = resolve(e0);
     Step st;
     lower(e, ViewChain{}, st);
@@ -343,8 +346,9 @@ class Planner {
       st.keep_alive.push_back(tmp);
     }
     psk_store_t out = nullptr;
-    check(backend().psk_eval((int32_t)st.sources.size(), st.sources.data(), (int32_t)st.prog.size(),
-                             st.prog.data(), (psk_dtype)e->dtype, eq, &out));
+    check((queued ? backend().psk_eval_async : backend().psk_eval)(
+        (int32_t)st.sources.size(), st.sources.data(), (int32_t)st.prog.size(), st.prog.data(), (psk_dtype)e->dtype,
+        eq, &out));
     return StoreRef(out);
   }
 };

@@ -453,4 +453,71 @@ __global__ void __launch_bounds__(kRedThreads) k_reduce_final(const RedAcc* part
   if (threadIdx.x == 0) *out = s_acc[0];
 }
 
+
+// ---- segmented reductions over runs (src/pyskip/reduce.py:8-33 with axis = 0) -------------
+// Segment j = flat coordinates [j L, (j + 1) L): the reduction of the fastest axis (or of all
+// inner axes at once) of a tensor.  One warp per segment: lane 0/1 find the first and last
+// run of the segment, the lanes stride over those runs with the piece of every run that lies
+// inside the segment (sum(val * len) with int32 wrap-around or fp64 accumulation, max, min,
+// prod(val^len)), a shuffle tree in fixed order folds the lanes.  One pass over the runs
+// (+ one search per segment) instead of log2(L) strided two-source evaluations.
+constexpr int kSegThreads = 256;
+
+template <bool IS_F>
+__global__ void __launch_bounds__(kSegThreads) k_reduce_segments(const int2* runs, int32_t nruns,
+                                                                 const int32_t* d_count, int32_t seg_len,
+                                                                 int32_t nseg, int op, uint32_t* out) {
+  const int lane = threadIdx.x & 31;
+  const int32_t j = (int32_t)((blockIdx.x * (long long)kSegThreads + threadIdx.x) >> 5);
+  if (j >= nseg) return;
+  if (d_count) nruns = ld_nc(d_count);
+  const int32_t s0 = j * seg_len, s1 = s0 + seg_len;
+  // first run whose end is > s0 (lane 0) / first run whose end is >= s1 (lane 1)
+  int32_t lo = 0, hi = nruns;
+  const int32_t key = lane == 0 ? s0 : s1 - 1;
+  if (lane < 2) {
+    while (lo < hi) {
+      const int32_t mid = lo + ((hi - lo) >> 1);
+      if (ld_nc(runs + mid).x <= key) lo = mid + 1; else hi = mid;
+    }
+  }
+  const int32_t r0 = __shfl_sync(0xffffffffu, lo, 0), r1 = __shfl_sync(0xffffffffu, lo, 1);
+  RedAcc acc;
+  acc.any = 0; acc.isum = 0; acc.fsum = 0; acc.mx = 0; acc.mn = 0;
+  for (int32_t i = r0 + lane; i <= r1; i += 32) {
+    const int2 r_ = ld_nc(runs + i);
+    const int32_t b = i > r0 ? ld_nc(runs + i - 1).x : s0;  // piece [max(begin, s0), min(end, s1))
+    const uint32_t len = (uint32_t)(imin(r_.x, s1) - imax(b, s0));
+    const uint32_t v = (uint32_t)r_.y;
+    RedAcc r;
+    r.any = 1; r.mx = v; r.mn = v;
+    if (op == PSK_RED_PROD) {
+      r.isum = ipow_wrap(v, len);
+      r.fsum = IS_F ? pow((double)u2f(v), (double)len) : 0.0;
+    } else {
+      r.isum = v * len;
+      r.fsum = IS_F ? (double)u2f(v) * (double)len : 0.0;
+    }
+    red_merge<IS_F>(acc, r, op);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    RedAcc o;
+    o.any = __shfl_down_sync(0xffffffffu, acc.any, d);
+    o.isum = __shfl_down_sync(0xffffffffu, acc.isum, d);
+    o.fsum = __shfl_down_sync(0xffffffffu, acc.fsum, d);
+    o.mx = __shfl_down_sync(0xffffffffu, acc.mx, d);
+    o.mn = __shfl_down_sync(0xffffffffu, acc.mn, d);
+    if (lane + d < 32) red_merge<IS_F>(acc, o, op);
+  }
+  if (lane == 0) {
+    uint32_t res;
+    if (op == PSK_RED_MAX) res = acc.mx;
+    else if (op == PSK_RED_MIN) res = acc.mn;
+    else if (IS_F) res = f2u((float)acc.fsum);
+    else res = acc.isum;
+    out[j] = res;
+  }
+}
+
 }  // namespace psk

@@ -54,10 +54,14 @@ constexpr int kTileSlack = 4 * PSK_MAX_SOURCES;
 constexpr int kTileRegion = kTileCap + kTileSlack;  // pairs per shared-memory region
 
 // dynamic shared memory of k_merge_eval: regions A | B (| C) of 8-byte pairs
-#ifndef PSK_TILE_REGIONS
-#define PSK_TILE_REGIONS 2
+constexpr int kTileRegions = 2;  // A: the tile's runs; B: the spans the threads keep
+#ifndef PSK_PARK_DEPTH
+#define PSK_PARK_DEPTH 4
 #endif
-constexpr int kTileRegions = PSK_TILE_REGIONS;  // 2: A + B; 3: A + B + C (spans parked for a whole tile)
+// Finished tiles whose place in the output is not known yet are parked in a per-CTA ring in
+// global memory (it stays in L2) and moved to their place a few tiles later, so a CTA never
+// waits for the slowest tile in front of it (see merge_eval_tile_loop)
+constexpr int kParkDepth = PSK_PARK_DEPTH;
 constexpr unsigned kMergeEvalSmemBytes = (unsigned)kTileRegions * kTileRegion * 8u;
 // CTAs that stay resident per SM (227 KB of shared memory, 2048 threads)
 constexpr int kCtasBySmem = (227 * 1024) / (int)(kMergeEvalSmemBytes + 6144);
@@ -541,6 +545,57 @@ PSK_D int32_t lookback_finish(unsigned long long* state, int32_t tile, int32_t c
   return excl;
 }
 
+// Non-blocking form: false (and nothing published) when an entry that is needed -- nearer than
+// the nearest PREFIX -- has not been published yet, or the window holds no PREFIX at all.
+template <int T>
+PSK_D bool lookback_try(unsigned long long* state, int32_t tile, int32_t count, const LookWords& lw, int32_t* excl_out,
+                        int32_t* s_sum, int32_t* s_has) {
+  constexpr int NW = T / 32;
+  constexpr int kLookW = LookW<T>::value;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int32_t excl = 0;
+  bool ok = true;
+  if (tile > 0) {
+    __syncthreads();  // s_sum / s_has free
+#pragma unroll
+    for (int u = 0; u < kLookW; ++u) {
+      const int32_t idx = tile - (1 + tid + T * u);
+      const unsigned long long w = lw.w[u];
+      const bool is_prefix = idx >= 0 ? (w >> 32) == ST_PREFIX : idx == -1;
+      const bool is_invalid = idx >= 0 && (w >> 32) == ST_INVALID;
+      const unsigned pmask = __ballot_sync(0xffffffffu, is_prefix);
+      const unsigned imask = __ballot_sync(0xffffffffu, is_invalid);
+      const int first = pmask ? (__ffs((int)pmask) - 1) : 32;
+      const unsigned upto = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);  // lanes 0..first
+      int32_t c = (lane <= first && idx >= 0) ? (int32_t)(uint32_t)w : 0;
+#pragma unroll
+      for (int dd = 16; dd > 0; dd >>= 1) c += __shfl_xor_sync(0xffffffffu, c, dd);
+      if (lane == 0) {
+        s_sum[u * NW + warp] = c;
+        // bit 0: piece holds a PREFIX; bit 1: an entry in front of it is still empty
+        s_has[u * NW + warp] = (pmask != 0 ? 1 : 0) | ((imask & upto) != 0 ? 2 : 0);
+      }
+    }
+    __syncthreads();
+    bool done = false;
+#pragma unroll
+    for (int q = 0; q < kLookW * NW; ++q) {
+      if (!done) {
+        const int32_t h = s_has[q];
+        excl += s_sum[q];
+        if (h & 2) ok = false;
+        done = (h & 1) != 0;
+      }
+    }
+    if (!done) ok = false;
+  }
+  if (ok && tid == 0)
+    st_volatile_u64(&state[(long long)tile * kStateStride],
+                    ((unsigned long long)ST_PREFIX << 32) | (uint32_t)(excl + count));
+  *excl_out = excl;
+  return ok;
+}
+
 // both steps at once (callers without anything to overlap)
 template <int T>
 PSK_D int32_t lookback_exclusive_cta(unsigned long long* state, int32_t tile, int32_t count, int32_t* s_sum,
@@ -690,8 +745,7 @@ template <int K, bool TYPED_FLOAT, int VIEWS, typename Eval>
 PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
   constexpr int T = kTileThreads;
   constexpr int RA = 0;                // region A: the bulk copies land here
-  constexpr int RB = kTileRegion;      // regions B, C: kept spans of alternating tiles
-  constexpr int RC = 2 * kTileRegion;
+  constexpr int RB = kTileRegion;      // region B: the spans the threads keep
 
   PSK_DYN_SMEM(smem_raw);
   const SmemPairs sm(smem_raw);
@@ -727,19 +781,19 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
   }
   __syncthreads();
 
-  // spans of the previous tile that still wait for their place in the output
-  int32_t pend_tile = -1, pend_total = 0, pend_n = 0, pend_base = 0, pend_ofs = 0, pend_region = 0;
-  LookWords pend_look;
+  // ---- parked tiles (no views): ring of kParkDepth slots of this CTA in global memory --------
+  __shared__ int32_t s_pk_tile[kParkDepth > 0 ? kParkDepth : 1], s_pk_total[kParkDepth > 0 ? kParkDepth : 1];
+  int pk_head = 0, pk_count = 0;   // oldest slot, parked tiles (uniform over the CTA)
+  int32_t look_tile = -1;          // tile whose look-back entries were requested last
+  LookWords look;
 #pragma unroll
-  for (int u = 0; u < kLookWMax; ++u) pend_look.w[u] = 0ull;
+  for (int u = 0; u < kLookWMax; ++u) look.w[u] = 0ull;
+  int2* const park = views ? nullptr : p->park + (long long)blockIdx.x * kParkDepth * kTileCap;
 
-  // global offset of a finished tile (decoupled look-back, its loads issued earlier), then
-  // every thread copies its own spans to their place in the output, 16 bytes per store
-  auto flush = [&](int32_t ftile, int32_t ftotal, int32_t fn, int32_t fbase, int32_t fofs, int fregion,
-                   const LookWords& look) {
-    const int32_t gofs = lookback_finish<T>(p->tile_state, ftile, ftotal, look, s_lbsum, s_lbhas);
+  PSK_PHASE_DECL;
+  // the last tile also leaves the run count and the sentinel pairs behind
+  auto finish_output = [&](int32_t ftile, int32_t cnt) {
     if (tid == 0 && ftile == n_tiles - 1) {
-      const int32_t cnt = gofs + ftotal;
       p->ctrl[CTRL_COUNT] = cnt;
       *p->out_count = cnt;  // the count stays on the device too (queued consumers)
       if (cnt <= p->out_capacity) {
@@ -747,27 +801,66 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
         p->out[cnt + 1] = make_int2(kSentinel, 0);
       }
     }
+  };
+  // every thread copies its own spans (shared region -> global), 16 bytes per store
+  auto store_spans = [&](int2* base_ptr, int32_t o, int src, int32_t fn) {
+    int2* const dst = base_ptr + o;
+    int32_t j = 0;
+    if (fn > 0 && (o & 1)) {  // 16-byte alignment of the vector stores
+      dst[0] = sm.ld(src);
+      j = 1;
+    }
+    for (; j + 1 < fn; j += 2) {
+      const int2 a = sm.ld(src + j), b = sm.ld(src + j + 1);
+      *reinterpret_cast<uint4*>(dst + j) = make_uint4((unsigned)a.x, (unsigned)a.y, (unsigned)b.x, (unsigned)b.y);
+    }
+    if (j < fn) dst[j] = sm.ld(src + j);
+  };
+  // with views: global offset by a blocking look-back, spans straight to their place
+  auto flush_direct = [&](int32_t ftile, int32_t ftotal, int32_t fn, int32_t fbase, int32_t fofs, int fregion) {
+    const int32_t gofs = lookback_exclusive_cta<T>(p->tile_state, ftile, ftotal, s_lbsum, s_lbhas);
+    finish_output(ftile, gofs + ftotal);
+    if (gofs + ftotal <= p->out_capacity) store_spans(p->out, gofs + fofs, fregion + fbase, fn);
+    else if (tid == 0) p->ctrl[CTRL_ERROR] = 2;
+    __syncthreads();  // the span region may be overwritten now
+  };
+  // the oldest parked tile moves to its place in the output if every tile in front of it has
+  // published its count (`block`: wait for that); coalesced 8-byte copies through L2
+  auto unpark = [&](bool block) -> bool {
+    const int32_t ftile = s_pk_tile[pk_head], ftotal = s_pk_total[pk_head];
+    int32_t gofs = 0;
+    bool ok = look_tile == ftile && lookback_try<T>(p->tile_state, ftile, ftotal, look, &gofs, s_lbsum, s_lbhas);
+    while (!ok && block) {
+      look = lookback_issue<T>(p->tile_state, ftile, 0);
+      look_tile = ftile;
+      ok = lookback_try<T>(p->tile_state, ftile, ftotal, look, &gofs, s_lbsum, s_lbhas);
+      if (!ok) sleep_ns(200);
+    }
+    look_tile = -1;
+    if (!ok) return false;
+    finish_output(ftile, gofs + ftotal);
     if (gofs + ftotal <= p->out_capacity) {
-      const int32_t o = gofs + fofs;
-      int2* const dst = p->out + o;
-      const int src = fregion + fbase;
-      int32_t j = 0;
-      if (fn > 0 && (o & 1)) {  // 16-byte alignment of the vector stores
-        dst[0] = sm.ld(src);
-        j = 1;
+      const int2* const src = park + (long long)pk_head * kTileCap;
+      int2* const dst = p->out + gofs;
+      // eight loads in flight per thread (every iteration of a plain copy loop would pay the
+      // L2 round trip again)
+      for (int32_t j0 = tid; j0 < ftotal; j0 += 8 * T) {
+        int2 r_[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (j0 + u * T < ftotal) r_[u] = ld_cg(src + j0 + u * T);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (j0 + u * T < ftotal) dst[j0 + u * T] = r_[u];
       }
-      for (; j + 1 < fn; j += 2) {
-        const int2 a = sm.ld(src + j), b = sm.ld(src + j + 1);
-        *reinterpret_cast<uint4*>(dst + j) = make_uint4((unsigned)a.x, (unsigned)a.y, (unsigned)b.x, (unsigned)b.y);
-      }
-      if (j < fn) dst[j] = sm.ld(src + j);
     } else if (tid == 0) {
       p->ctrl[CTRL_ERROR] = 2;
     }
-    __syncthreads();  // the span region may be overwritten now
+    pk_head = (pk_head + 1) % (kParkDepth > 0 ? kParkDepth : 1);
+    --pk_count;
+    return true;
   };
 
-  PSK_PHASE_DECL;
   for (int it = 0;; ++it) {
     const TileDesc& d = s_desc[it & 1];
     TileLayout& lay = s_layout[it & 1];
@@ -782,7 +875,10 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     int32_t ticket = 0;
     if (warp == 0) ticket = take_ticket(p);
     mbar_wait(&s_bar, (uint32_t)(it & 1));
-    if (pend_tile >= 0) pend_look = lookback_issue<T>(p->tile_state, pend_tile, 0);
+    if (pk_count > 0) {
+      look_tile = s_pk_tile[pk_head];
+      look = lookback_issue<T>(p->tile_state, look_tile, 0);
+    }
     PSK_PHASE(0);
 
     // ---- with views: map the raw ends through the view chains and squeeze out the runs
@@ -919,13 +1015,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     fetched.tile = 0;
     if (warp == 0) fetched = fetch_tile_desc(p, k, n_tiles, views, ticket);
 
-    // ---- two regions: the previous tile's spans leave region B now ------------------------
-    if (kTileRegions == 2 && pend_tile >= 0) {
-      flush(pend_tile, pend_total, pend_n, pend_base, pend_ofs, pend_region, pend_look);
-      pend_tile = -1;
-    }
-    PSK_PHASE(5);
-    const int WR = views ? RA : ((kTileRegions == 3 && (it & 1)) ? RC : RB);
+    const int WR = views ? RA : RB;
     const uint32_t out_begin = sm.at(WR + base);
     uint32_t out_at = out_begin;  // where this thread's next kept span goes
 
@@ -974,29 +1064,33 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     if (tid == 0) publish_aggregate(p->tile_state, tile, tile_total);
     const bool next_valid = s_desc[(it + 1) & 1].tile < n_tiles;
     if (!views) {
+      // park the tile's spans (dense, in tile order) in this CTA's ring; a full ring first
+      // waits for its oldest tile
+      if (pk_count == kParkDepth) unpark(true);
+      const int slot = (pk_head + pk_count) % kParkDepth;
+      store_spans(park + (long long)slot * kTileCap, my_ofs, WR + base, n);
+      if (tid == 0) {
+        s_pk_tile[slot] = tile;
+        s_pk_total[slot] = tile_total;
+      }
+      ++pk_count;
       if (warp == 0 && next_valid)
         issue_tile_copies(p, s_desc[(it + 1) & 1], k, sm, RA, &s_layout[(it + 1) & 1], &s_bar);
-      // three regions: the PREVIOUS tile's spans leave their region now
-      if (kTileRegions == 3 && pend_tile >= 0)
-        flush(pend_tile, pend_total, pend_n, pend_base, pend_ofs, pend_region, pend_look);
-      else
-        __syncthreads();  // the next tile's layout is visible to everybody
-      pend_tile = tile;
-      pend_total = tile_total;
-      pend_n = n;
-      pend_base = base;
-      pend_ofs = my_ofs;
-      pend_region = WR;
+      __syncthreads();  // region B is free, the parked spans and the next layout are visible
+      PSK_PHASE(6);
+      // the oldest parked tile leaves if its place is known by now (entries requested at the
+      // top of this iteration); never waits here
+      if (look_tile >= 0 && look_tile == s_pk_tile[pk_head]) unpark(false);
+      PSK_PHASE(5);
     } else {
-      flush(tile, tile_total, n, base, my_ofs, WR, lookback_issue<T>(p->tile_state, tile, 0));
+      flush_direct(tile, tile_total, n, base, my_ofs, WR);
       if (warp == 0 && next_valid)
         issue_tile_copies(p, s_desc[(it + 1) & 1], k, sm, RA, &s_layout[(it + 1) & 1], &s_bar);
       __syncthreads();
+      PSK_PHASE(6);
     }
-    PSK_PHASE(6);
   }
-  if (pend_tile >= 0)
-    flush(pend_tile, pend_total, pend_n, pend_base, pend_ofs, pend_region, lookback_issue<T>(p->tile_state, pend_tile, 0));
+  while (pk_count > 0) unpark(true);
   PSK_PHASE_FLUSH;
 }
 

@@ -215,7 +215,7 @@ bool compile_cubin(int K, bool typed_float, bool views, int T, int CAP, int regi
   }
   const std::string opt_t = "-DPSK_TILE_THREADS=" + std::to_string(T);
   const std::string opt_c = "-DPSK_TILE_CAP=" + std::to_string(CAP);
-  const std::string opt_r = "-DPSK_TILE_REGIONS=" + std::to_string(regions);
+  const std::string opt_r = "-DPSK_PARK_DEPTH=" + std::to_string(regions);
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo",
 #ifdef PSK_PHASE_TIMING
                         "-DPSK_PHASE_TIMING",

@@ -66,6 +66,7 @@ struct DPlan {
   int32_t* ctrl;                   // [0]=ticket [1]=out_count [2]=error
   unsigned long long* phase;       // [8] cycle counters (PSK_PHASE_TIMING builds only)
   unsigned long long* trace;       // [max_tiles * 8] per-tile globaltimer stamps (same builds)
+  int2* park;                      // [grid * kParkDepth * kTileCap] parked spans (no views)
   int2* out;                       // result pairs [out_capacity + 4]
   int32_t* out_count;              // the result's run count, left on the device for consumers
   psk_node prog[PSK_MAX_PROGRAM];

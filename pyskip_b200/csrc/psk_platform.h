@@ -58,6 +58,15 @@ PSK_D int2 ld_nc(const int2* p) {
 #endif
 }
 
+// load that bypasses L1 (data written by other threads of the SM through L2)
+PSK_D int2 ld_cg(const int2* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
+
 // predicated read-only load: *p if take, else dflt -- one @p LDG, never a branch
 PSK_D int32_t ld_nc_if(const int32_t* p, bool take, int32_t dflt) {
 #if defined(__CUDA_ARCH__)

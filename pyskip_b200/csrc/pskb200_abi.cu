@@ -62,7 +62,7 @@ struct Ctx {
   bool convert_vec = false;        // dense <-> RLE with 16-byte accesses (psk_set_vector_conversion)
   int64_t small_partition = 2048;  // samples up to which one block does the whole partition
   int stagger_ns = 0;
-  int jit_T = kTileThreads, jit_CAP = kTileCap, jit_regions = kTileRegions;  // tile geometry of the specialised kernels (PSKB200_TILE_*)
+  int jit_T = kTileThreads, jit_CAP = kTileCap, jit_regions = kParkDepth;  // tile geometry / park depth of the specialised kernels (PSKB200_TILE_*)
   cudaEvent_t xev = nullptr;                     // orders the download stream behind the library stream
   unsigned long long* trace_buf = nullptr;  // PSK_PHASE_TIMING builds: device trace buffer
   int64_t trace_cap = 0, trace_tiles = 0;
@@ -169,9 +169,9 @@ psk_status do_init(int device) {
     const int t = atoi(sv);
     if (t >= 32 && t <= 1024 && t % 32 == 0) g.jit_T = t;
   }
-  if (const char* sv = getenv("PSKB200_TILE_REGIONS")) {
+  if (const char* sv = getenv("PSKB200_PARK_DEPTH")) {
     const int r = atoi(sv);
-    if (r == 2 || r == 3) g.jit_regions = r;
+    if (r >= 1 && r <= 16) g.jit_regions = r;
   }
   if (const char* sv = getenv("PSKB200_TILE_CAP")) {
     const int c = atoi(sv);
@@ -360,6 +360,18 @@ __global__ void k_deinterleave(const int2* runs, int32_t n, int32_t* ends, void*
     ends[i] = r.x;
     if (ELEM == 4) reinterpret_cast<uint32_t*>(vals)[i] = (uint32_t)r.y;
     else reinterpret_cast<uint8_t*>(vals)[i] = (uint8_t)r.y;
+  }
+}
+
+// pairs already in the store layout (another GPU's runs, received into a device buffer): copy +
+// validate; the ends are shifted by `offset`
+__global__ void k_copy_pairs(const int2* in, int32_t n, int32_t offset, int2* out, int32_t* flag) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int2 r = in[i];
+    const int32_t prev = i ? in[i - 1].x : 0;
+    if (flag && r.x <= prev) atomicOr(flag, 1);
+    out[i] = make_int2(r.x + offset, r.y);
   }
 }
 
@@ -600,8 +612,8 @@ psk_status psk_set_tile_geometry(int32_t threads, int32_t cap, int32_t regions) 
   std::lock_guard<std::recursive_mutex> api_lock_(g.api_mu);
   PSK_CHECK_ARG(threads >= 32 && threads <= 1024 && threads % 32 == 0);
   PSK_CHECK_ARG(cap >= 512 && cap <= 13000 && cap % 64 == 0);
-  PSK_CHECK_ARG(regions == 2 || regions == 3);
-  PSK_CHECK_ARG((size_t)regions * (size_t)(cap + kTileSlack) * 8u + 6144 <= 227 * 1024);
+  PSK_CHECK_ARG(regions >= 1 && regions <= 16);  // park depth
+  PSK_CHECK_ARG((size_t)kTileRegions * (size_t)(cap + kTileSlack) * 8u + 6144 <= 227 * 1024);
   g.jit_T = threads;
   g.jit_CAP = cap;
   g.jit_regions = regions;
@@ -781,6 +793,70 @@ psk_status psk_store_from_device_runs(psk_dtype dtype, int64_t nruns, const int3
   return PSK_OK;
 }
 
+psk_status psk_store_export_pairs(psk_store_t s, void* d_pairs) {
+  NEED_INIT();
+  PSK_CHECK_ARG(s != nullptr && d_pairs != nullptr);
+  READY(s);
+  CUDA_TRY(cudaMemcpyAsync(d_pairs, s->d_runs, (size_t)s->nruns * 8, cudaMemcpyDeviceToDevice, g.stream));
+  return PSK_OK;
+}
+
+psk_status psk_store_from_device_pairs(psk_dtype dtype, int64_t nruns, const void* d_pairs, psk_store_t* out) {
+  NEED_INIT();
+  PSK_CHECK_ARG(out != nullptr && d_pairs != nullptr);
+  PSK_CHECK_ARG(dtype >= PSK_I32 && dtype <= PSK_CHAR);
+  PSK_CHECK_ARG(nruns > 0 && nruns < 0x7fffffffLL);
+  psk_store_t s;
+  psk_status st = new_store(dtype, nruns, &s);
+  if (st != PSK_OK) return st;
+  int32_t* d_flag = nullptr;
+  st = dmalloc(reinterpret_cast<void**>(&d_flag), 16);
+  if (st != PSK_OK) {
+    psk_store_release(s);
+    return st;
+  }
+  cudaMemsetAsync(d_flag, 0, 16, g.stream);
+  LAUNCH(k_copy_pairs, (unsigned)((nruns + 255) / 256), 256, 0, reinterpret_cast<const int2*>(d_pairs), (int32_t)nruns, 0,
+         s->d_runs, d_flag);
+  LAUNCH(k_seal, 1, 32, 0, s->d_runs, (int32_t)nruns, s->d_count);
+  st = finish_runs_store(s, nruns, d_flag);
+  if (st != PSK_OK) {
+    psk_store_release(s);
+    return st;
+  }
+  *out = s;
+  return PSK_OK;
+}
+
+psk_status psk_store_concat(int32_t n, const psk_store_t* parts, psk_store_t* out) {
+  NEED_INIT();
+  PSK_CHECK_ARG(n >= 1 && parts != nullptr && out != nullptr);
+  int64_t total = 0, span = 0;
+  for (int i = 0; i < n; ++i) {
+    PSK_CHECK_ARG(parts[i] != nullptr);
+    READY(parts[i]);
+    PSK_CHECK_ARG(parts[i]->dtype == parts[0]->dtype);
+    total += parts[i]->nruns;
+    span += parts[i]->span;
+  }
+  PSK_CHECK_ARG(span <= 0x7fffffffLL && total < 0x7fffffffLL);
+  psk_store_t s;
+  psk_status st = new_store(parts[0]->dtype, total, &s);
+  if (st != PSK_OK) return st;
+  int64_t r = 0, off = 0;
+  for (int i = 0; i < n; ++i) {
+    LAUNCH(k_copy_pairs, (unsigned)((parts[i]->nruns + 255) / 256), 256, 0, parts[i]->d_runs, (int32_t)parts[i]->nruns,
+           (int32_t)off, s->d_runs + r, (int32_t*)nullptr);
+    r += parts[i]->nruns;
+    off += parts[i]->span;
+  }
+  LAUNCH(k_seal, 1, 32, 0, s->d_runs, (int32_t)total, s->d_count);
+  s->nruns = total;
+  s->span = (int32_t)span;
+  *out = s;
+  return PSK_OK;
+}
+
 psk_status psk_store_fill(psk_dtype dtype, int32_t span, uint32_t fill_bits, psk_store_t* out) {
   NEED_INIT();
   PSK_CHECK_ARG(out != nullptr);
@@ -898,6 +974,7 @@ int64_t psk_store_nruns(psk_store_t s) {
   return s->nruns;
 }
 int32_t psk_store_span(psk_store_t s) { return s ? s->span : 0; }
+int32_t psk_store_pending(psk_store_t s) { return (s && s->pending_slot >= 0) ? 1 : 0; }
 int32_t psk_store_dtype(psk_store_t s) { return s ? s->dtype : -1; }
 
 psk_status psk_store_device_pairs(psk_store_t s, const void** d_pairs) {
@@ -1058,7 +1135,7 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
   hp.on_device = on_device ? 1 : 0;
 
   // ---- which kernel: the specialised one (NVRTC) for large evaluations ---------------------
-  int T = kTileThreads, CAP = kTileCap, regions = kTileRegions;
+  int T = kTileThreads, CAP = kTileCap, park_depth = kParkDepth;
 #ifndef PSK_CPU_SIM
   const JitKernel* jk = nullptr;
   if (total_runs >= g.jit_min_runs) {
@@ -1067,11 +1144,11 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
     if (jk) {
       T = g.jit_T;
       CAP = g.jit_CAP;
-      regions = g.jit_regions;
+      park_depth = g.jit_regions;
     }
   }
 #endif
-  const size_t smem = (size_t)regions * (size_t)(CAP + kTileSlack) * 8u;
+  const size_t smem = (size_t)kTileRegions * (size_t)(CAP + kTileSlack) * 8u;
   int ctas = (int)((227 * 1024) / (smem + 6144));
   if (ctas > 2048 / T) ctas = 2048 / T;
   if (ctas < 1) ctas = 1;
@@ -1117,7 +1194,13 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
   size_t o_la = (o_hi + (size_t)max_tiles * 4 + 15) & ~(size_t)15;
   size_t o_plan = (o_la + (any_views ? (size_t)max_tiles * k * 16 : 0) + 15) & ~(size_t)15;
   const size_t plan_bytes = offsetof(DPlan, src) + sizeof(DSource) * (size_t)k;
-  size_t scratch_bytes = o_plan + sizeof(DPlan);
+  // persistent grid: as many CTAs as stay resident (shared memory / thread limits)
+  int64_t grid = (int64_t)ctas * g.sm_count;
+  if (grid > max_tiles) grid = max_tiles;
+  // ring of parked tiles per CTA (no views): park_depth slots of CAP pairs
+  const size_t o_park = (o_plan + sizeof(DPlan) + 255) & ~(size_t)255;
+  const size_t park_bytes = any_views ? 0 : (size_t)grid * (size_t)park_depth * (size_t)CAP * 8u;
+  size_t scratch_bytes = o_park + park_bytes;
   unsigned char* scratch = nullptr;
   st = dmalloc(reinterpret_cast<void**>(&scratch), scratch_bytes);
   if (st != PSK_OK) return st;
@@ -1134,6 +1217,7 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
   hp.bounds = reinterpret_cast<int32_t*>(scratch + o_bounds);
   hp.tile_hi = reinterpret_cast<int32_t*>(scratch + o_hi);
   hp.lookahead = reinterpret_cast<int2*>(scratch + o_la);
+  hp.park = reinterpret_cast<int2*>(scratch + o_park);
   hp.out = res->d_runs;
   hp.out_count = res->d_count;
   hp.out_capacity = (int32_t)total_runs;
@@ -1148,9 +1232,6 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
     int64_t pgrid = (max_samples + kPartBlock - 1) / kPartBlock;
     if (pgrid < 1) pgrid = 1;
     LAUNCH(k_partition, (unsigned)pgrid, kPartBlock, 0, d_plan);
-    // persistent grid: as many CTAs as stay resident (shared memory / thread limits)
-    int64_t grid = (int64_t)ctas * g.sm_count;
-    if (grid > max_tiles) grid = max_tiles;
     if (g.profile) cudaEventRecord(deferred ? g.slots[slot].t0 : g.pev0, g.stream);
     bool launched = false;
 #ifndef PSK_CPU_SIM
@@ -1433,6 +1514,32 @@ psk_status psk_reduce(psk_store_t s, psk_reduce_op op, uint64_t* result_bits) {
   else if (is_f) memcpy(result_bits, &h->fsum, 8);
   else *result_bits = h->isum;
   return PSK_OK;
+}
+
+psk_status psk_reduce_segments(psk_store_t s, int32_t seg_len, psk_reduce_op op, psk_store_t* out) {
+  NEED_INIT();
+  PSK_CHECK_ARG(s != nullptr && out != nullptr);
+  PSK_CHECK_ARG(op >= PSK_RED_SUM && op <= PSK_RED_PROD);
+  PSK_CHECK_ARG(s->dtype == PSK_I32 || s->dtype == PSK_F32);
+  PSK_CHECK_ARG(seg_len > 0 && s->span % seg_len == 0);
+  const bool queued = s->pending_slot >= 0 && !s->failed;
+  if (!queued) READY(s);
+  const int32_t nseg = s->span / seg_len;
+  uint32_t* d_dense = nullptr;
+  psk_status st = dmalloc(reinterpret_cast<void**>(&d_dense), (size_t)nseg * 4);
+  if (st != PSK_OK) return st;
+  const unsigned grid = (unsigned)(((long long)nseg * 32 + kSegThreads - 1) / kSegThreads);
+  const int32_t nmax = (int32_t)(queued ? s->capacity : s->nruns);
+  if (s->dtype == PSK_F32)
+    LAUNCH(k_reduce_segments<true>, grid, kSegThreads, 0, s->d_runs, nmax, queued ? s->d_count : nullptr, seg_len, nseg,
+           (int)op, d_dense);
+  else
+    LAUNCH(k_reduce_segments<false>, grid, kSegThreads, 0, s->d_runs, nmax, queued ? s->d_count : nullptr, seg_len, nseg,
+           (int)op, d_dense);
+  // the per-segment values, run-length encoded (TYPED equality, as from_buffer: conv.hpp:21-25)
+  st = psk_store_from_dense_device((psk_dtype)s->dtype, nseg, d_dense, out);
+  cudaFreeAsync(d_dense, g.stream);
+  return st;
 }
 
 psk_status psk_store_slice(psk_store_t s, int32_t start, int32_t stop, psk_store_t* out) {

@@ -10,20 +10,31 @@ eval::fuse_stores (:568-607):
     offset, so spans beyond 2^31 (BASELINE configs 4 and 5) are representable;
   * element-wise evaluation of co-partitioned operands needs no communication at all;
   * stitching is one tiny all-gather of (first value, last value, run count) per rank: a
-    shard drops its last run when the next non-empty shard starts with an equal value
-    (eval.hpp:581-588) and an exclusive scan of the surviving counts gives global run offsets;
+    shard drops its last run when the next shard starts with an equal value
+    (eval.hpp:581-588) and an exclusive scan of the surviving counts gives global run offsets.
+    The triples are produced ON THE DEVICE (psk_store_boundary_device reads the count of a
+    still-queued result there), several steps can be batched into one collective
+    (BoundaryStitcher), and nothing but the gathered triples ever reaches the host;
   * reductions are a local one-pass reduction + one scalar all-reduce;
   * the 3-D convolution partitions the slowest axis (z) into slabs and exchanges one boundary
-    z-slice per neighbour AS RUNS (ends + values), edge ranks use the fill value.
+    z-slice per neighbour AS RUNS: the slice is cut out on the device (psk_store_slice),
+    the exact run counts are exchanged first, then exactly that many (end, value) pairs go
+    device to device (psk_store_export_pairs -> send / recv -> psk_store_from_device_pairs),
+    the halo slices are put around the slab (psk_store_concat) and one stencil launch
+    (psk_conv_nd, no padding along z) produces the rank's output slab.  Edge ranks use the
+    fill value.
 
 The collectives move a few words (stitch, reductions) or the runs of a single z-slice
-(halo), so they are latency- not bandwidth-bound; there is no compute kernel whose tiles
-feed a collective, hence no fused compute+collective kernel on this path.
+(halo, ~0.1 % of a slab), so they are latency- not bandwidth-bound; there is no compute
+kernel whose tiles feed a collective, hence no fused compute+collective kernel on this path.
+All library work is issued on torch's current CUDA stream (use_torch_stream), so NCCL
+operations and library kernels are ordered on one timeline without host synchronisation.
 """
 from __future__ import annotations
 
 import numpy as np
 
+from . import _abi
 from . import _pyskip_b200_ext as _ext
 from .tensor import Tensor
 from .util import broadcast_shape
@@ -44,33 +55,102 @@ def shard_bounds(span: int, rank: int, size: int):
     return (rank * span) // size, ((rank + 1) * span) // size
 
 
+def _on_gpu():
+    dist = _dist()
+    return dist.is_initialized() and dist.get_backend() == "nccl"
+
+
 def _device():
     import torch
-    dist = _dist()
-    if dist.is_initialized() and dist.get_backend() == "nccl":
+    if _on_gpu():
         return torch.device("cuda", torch.cuda.current_device())
     return torch.device("cpu")
 
 
-def _all_gather_i64(values):
+def _lib():
+    """ctypes binding of the library the extension is bound to (same loaded instance)."""
+    path = _ext._backend_path()
+    lib = _LIBS.get(path)
+    if lib is None:
+        lib = _LIBS[path] = _abi.Lib(path)
+    return lib
+
+
+_LIBS = {}
+
+
+def use_torch_stream():
+    """Issue all library work on torch's current CUDA stream (call once per process after
+    torch.cuda.set_device): collectives and library kernels then share one timeline."""
     import torch
-    dist = _dist()
-    rank, size = world()
-    mine = torch.tensor(list(values), dtype=torch.int64, device=_device())
-    if size == 1:
-        return mine.cpu().numpy()[None, :]
-    out = torch.empty(size * len(values), dtype=torch.int64, device=_device())
-    dist.all_gather_into_tensor(out, mine)
-    return out.cpu().numpy().reshape(size, len(values))
+    if _on_gpu() or torch.cuda.is_available():
+        _lib().set_stream(torch.cuda.current_stream().cuda_stream)
 
 
 _NP_OF = {int: np.int32, float: np.float32, bool: np.bool_}
+_ARRAY_OF = {int: "IntArray", float: "FloatArray", bool: "BoolArray"}
+_ABI_DTYPE = {int: _abi.I32, float: _abi.F32, bool: _abi.BOOL}
 
 
-def _payload_bits(vals: np.ndarray) -> np.ndarray:
-    if vals.dtype == np.float32:
-        return vals.view(np.uint32).astype(np.int64)
-    return vals.astype(np.int64) & 0xFFFFFFFF
+def _handle(t: Tensor) -> _abi.Store:
+    """The evaluated store of a tensor as an owning ctypes handle."""
+    return _abi.Store(_lib(), t.to_array()._store_handle())
+
+
+def _adopt(store: _abi.Store, shape, dtype) -> Tensor:
+    """A tensor over a store produced through the ctypes binding (ownership moves)."""
+    h, store.h = store.h, None
+    arr = getattr(_ext, _ARRAY_OF[dtype])._adopt_store(h)
+    return Tensor(shape=tuple(shape), val=arr, dtype=dtype)
+
+
+class BoundaryStitcher:
+    """fuse_stores across ranks (eval.hpp:581-588), batched: every add() appends the shard's
+    (first value, last value, run count) to a device buffer with one tiny library kernel --
+    no host synchronisation, works on still-queued results -- and drain() exchanges all
+    pending triples with ONE all-gather and applies the drop rule."""
+
+    def __init__(self, batch=32):
+        import torch
+        self.rank, self.size = world()
+        self.batch = int(batch)
+        self.pending = 0
+        self.mine = torch.zeros(self.batch * 3, dtype=torch.int64, device=_device())
+        self.all = torch.zeros(self.size * self.batch * 3, dtype=torch.int64, device=_device())
+        self.last = None
+
+    def add(self, store):
+        """store: _abi.Store (or raw handle) of this rank's shard for one step."""
+        _lib().store_boundary_device(store, self.mine.data_ptr() + 24 * self.pending)
+        self.pending += 1
+        if self.pending == self.batch:
+            self.drain()
+
+    def drain(self):
+        """-> list of (keep, first_index, total) per pending step for this rank (also kept in
+        .last); empty when nothing was pending."""
+        n = self.pending
+        if n == 0:
+            return []
+        dist = _dist()
+        if self.size > 1:
+            if not _on_gpu():
+                _lib().synchronize()
+            dist.all_gather_into_tensor(self.all[:self.size * n * 3], self.mine[:n * 3])
+            table = self.all[:self.size * n * 3].view(self.size, n, 3).cpu().numpy()
+        else:
+            _lib().synchronize()
+            table = self.mine[:n * 3].view(1, n, 3).cpu().numpy()
+        out = []
+        for s in range(n):
+            counts = table[:, s, 2].copy()
+            for r in range(self.size - 1):
+                if table[r, s, 1] == table[r + 1, s, 0]:
+                    counts[r] -= 1          # eval.hpp:581-588
+            out.append((int(counts[self.rank]), int(counts[:self.rank].sum()), int(counts.sum())))
+        self.pending = 0
+        self.last = out[-1]
+        return out
 
 
 class ShardedTensor:
@@ -110,36 +190,48 @@ class ShardedTensor:
     def stitch(self, bitwise=True):
         """-> (runs this rank contributes, global index of its first run, global run count).
         A rank's last run is dropped when the next shard starts with an equal value.  Only the
-        first / last value and the run count of every shard are exchanged; nothing is copied
-        to the host."""
+        first / last value and the run count of every shard are exchanged, as one triple that
+        is assembled on the device."""
         src = self.local.eval() if bitwise else self.local
-        n = len(src)
-        nruns = src.to_array().rle_length()
-        first = np.asarray([src[0]], dtype=_NP_OF[self.local.dtype])
-        last = np.asarray([src[n - 1]], dtype=_NP_OF[self.local.dtype])
-        table = _all_gather_i64([int(_payload_bits(first)[0]), int(_payload_bits(last)[0]), nruns])
-        counts = table[:, 2].copy()
-        for r in range(self.size - 1):
-            if table[r, 1] == table[r + 1, 0]:
-                counts[r] -= 1          # eval.hpp:581-588
+        st = BoundaryStitcher(batch=1)
         self._evaluated = src
-        return int(counts[self.rank]), int(counts[:self.rank].sum()), int(counts.sum())
+        self._store = _handle(src)
+        st.add(self._store)             # batch of 1: drains at once
+        return st.last
 
     def gather_global(self, bitwise=True):
-        """All ranks -> the global (int64 ends, vals) run arrays (tests / small outputs)."""
+        """All ranks -> the global (int64 ends, vals) run arrays (tests / small outputs): the
+        kept runs of every shard travel as (end, value) pairs through one all-gather of
+        counts and one all-gather of padded pair buffers."""
         import torch
         dist = _dist()
         keep, _, total = self.stitch(bitwise)
         ends, vals = self._evaluated.to_runs()
-        ends, vals = ends[:keep], vals[:keep]
+        ends, vals = np.asarray(ends)[:keep], np.asarray(vals)[:keep]
         gl = ends.astype(np.int64) + self.offset
         if self.size == 1:
             return gl, vals
-        objs = [None] * self.size
-        dist.all_gather_object(objs, (gl, vals))
+        dev = _device()
+        counts = torch.zeros(self.size, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, torch.tensor([keep], dtype=torch.int64, device=dev))
+        counts = counts.cpu().numpy()
+        cap = int(counts.max())
+        bits = vals.view(np.uint32).astype(np.int64) if vals.dtype == np.float32 else vals.astype(np.int64)
+        mine = torch.zeros(2 * cap, dtype=torch.int64, device=dev)
+        mine[:keep] = torch.from_numpy(gl).to(dev)
+        mine[cap:cap + keep] = torch.from_numpy(bits).to(dev)
+        allb = torch.zeros(self.size * 2 * cap, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allb, mine)
+        allb = allb.cpu().numpy().reshape(self.size, 2, cap)
+        g_ends = np.concatenate([allb[r, 0, :counts[r]] for r in range(self.size)])
+        g_bits = np.concatenate([allb[r, 1, :counts[r]] for r in range(self.size)])
+        if vals.dtype == np.float32:
+            g_vals = g_bits.astype(np.uint32).view(np.float32)
+        else:
+            g_vals = g_bits.astype(vals.dtype)
         # a dropped last run extends its successor: the successor's run simply starts earlier,
         # which the end-only encoding expresses by the drop itself
-        return np.concatenate([o[0] for o in objs]), np.concatenate([o[1] for o in objs])
+        return g_ends, g_vals
 
     # ---- reductions -----------------------------------------------------------------------
     def sum(self):
@@ -178,67 +270,59 @@ class ShardedTensor:
 
 # ---- z-slab convolution with halo exchange ------------------------------------------------
 
-def _exchange_slices(lo_slice: Tensor, hi_slice: Tensor):
-    """Send my lowest z-slice to rank-1 and my highest to rank+1 (as runs); receive theirs.
-    Returns (slice from rank-1 or None, slice from rank+1 or None)."""
+def exchange_halo(store, plane: int, span: int, dtype, fill):
+    """Boundary z-slices of a slab as stores: -> (slice of rank-1, slice of rank+1), each of
+    `plane` elements; edge ranks get the fill value.  The lowest / highest slice of `store`
+    (span = slab length) is cut out on the device, the run counts are exchanged first, then
+    exactly that many (end, value) pairs move device to device."""
     import torch
     dist = _dist()
+    lib = _lib()
     rank, size = world()
     dev = _device()
-
-    def pack(t):
-        e, v = t.to_runs()
-        v32 = v.view(np.int32) if v.dtype == np.float32 else v.astype(np.int32)
-        return torch.from_numpy(np.concatenate([[len(e)], e, v32]).astype(np.int32)).to(dev)
-
-    def unpack(buf, like: Tensor, shape):
-        a = buf.cpu().numpy()
-        n = int(a[0])
-        e, v = a[1:1 + n], a[1 + n:1 + 2 * n]
-        if like.dtype is float:
-            arr = _ext.FloatArray._from_runs(e, v.view(np.float32))
-        elif like.dtype is bool:
-            arr = _ext.BoolArray._from_runs(e, v.astype(np.bool_))
-        else:
-            arr = _ext.IntArray._from_runs(e, v)
-        return Tensor(shape=shape, val=arr)
-
-    plane = lo_slice.shape
-    cap = 2 * int(np.prod(plane)) + 1              # worst case: one run per voxel
-    from_lo = from_hi = None
-    ops, bufs = [], {}
+    adt = _ABI_DTYPE[dtype]
+    fill_store = lambda: lib.store_fill(adt, plane, dtype(fill))
+    if size == 1:
+        return fill_store(), fill_store()
+    lo = lib.store_slice(store, 0, plane) if rank > 0 else None
+    hi = lib.store_slice(store, span - plane, span) if rank < size - 1 else None
+    # 1) run counts to the neighbours
+    cnt_send = torch.tensor([lo.nruns if lo else 0, hi.nruns if hi else 0], dtype=torch.int64, device=dev)
+    cnt_recv = torch.zeros(2, dtype=torch.int64, device=dev)      # [from rank-1, from rank+1]
+    ops = []
     if rank > 0:
-        bufs["send_lo"] = pack(lo_slice)
-        bufs["recv_lo"] = torch.zeros(cap, dtype=torch.int32, device=dev)
-        ops.append(dist.P2POp(dist.isend, _padded(bufs["send_lo"], cap, dev), rank - 1))
-        ops.append(dist.P2POp(dist.irecv, bufs["recv_lo"], rank - 1))
+        ops += [dist.P2POp(dist.isend, cnt_send[0:1], rank - 1), dist.P2POp(dist.irecv, cnt_recv[0:1], rank - 1)]
     if rank < size - 1:
-        bufs["send_hi"] = pack(hi_slice)
-        bufs["recv_hi"] = torch.zeros(cap, dtype=torch.int32, device=dev)
-        ops.append(dist.P2POp(dist.isend, _padded(bufs["send_hi"], cap, dev), rank + 1))
-        ops.append(dist.P2POp(dist.irecv, bufs["recv_hi"], rank + 1))
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
+        ops += [dist.P2POp(dist.isend, cnt_send[1:2], rank + 1), dist.P2POp(dist.irecv, cnt_recv[1:2], rank + 1)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    n_lo, n_hi = (int(v) for v in cnt_recv.cpu().numpy())
+    # 2) exactly that many pairs
+    bufs, ops = {}, []
     if rank > 0:
-        from_lo = unpack(bufs["recv_lo"], lo_slice, plane)
+        bufs["s_lo"] = torch.empty(2 * lo.nruns, dtype=torch.int32, device=dev)
+        lib.store_export_pairs(lo, bufs["s_lo"].data_ptr())
+        bufs["r_lo"] = torch.empty(2 * n_lo, dtype=torch.int32, device=dev)
+        ops += [dist.P2POp(dist.isend, bufs["s_lo"], rank - 1), dist.P2POp(dist.irecv, bufs["r_lo"], rank - 1)]
     if rank < size - 1:
-        from_hi = unpack(bufs["recv_hi"], hi_slice, plane)
-    return from_lo, from_hi
-
-
-def _padded(buf, cap, dev):
-    import torch
-    out = torch.zeros(cap, dtype=torch.int32, device=dev)
-    out[:buf.numel()] = buf
-    return out
+        bufs["s_hi"] = torch.empty(2 * hi.nruns, dtype=torch.int32, device=dev)
+        lib.store_export_pairs(hi, bufs["s_hi"].data_ptr())
+        bufs["r_hi"] = torch.empty(2 * n_hi, dtype=torch.int32, device=dev)
+        ops += [dist.P2POp(dist.isend, bufs["s_hi"], rank + 1), dist.P2POp(dist.irecv, bufs["r_hi"], rank + 1)]
+    if not _on_gpu():
+        lib.synchronize()               # (CPU tests: the export is a plain memcpy)
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    below = lib.store_from_device_pairs(adt, n_lo, bufs["r_lo"].data_ptr()) if rank > 0 else fill_store()
+    above = lib.store_from_device_pairs(adt, n_hi, bufs["r_hi"].data_ptr()) if rank < size - 1 else fill_store()
+    return below, above
 
 
 def conv_3d_slab(local: Tensor, kernel: Tensor, padding=0, fill=0):
     """conv_3d (src/pyskip/convolve.py:39-59) of a volume partitioned along z: `local` is
-    this rank's z-slab (shape (X, Y, Zloc)).  Requires an odd kernel with padding =
-    kernel // 2 along z (the "same" convolution of the BASELINE configs), so every rank's
-    output slab has the thickness of its input slab."""
+    this rank's z-slab (shape (X, Y, Zloc)).  Requires a 3x3x3 kernel with padding 1 along z
+    (the "same" convolution of the BASELINE configs), so every rank's output slab has the
+    thickness of its input slab."""
     from .convolve import conv_3d
     rank, size = world()
     kx, ky, kz = kernel.shape
@@ -248,13 +332,14 @@ def conv_3d_slab(local: Tensor, kernel: Tensor, padding=0, fill=0):
     assert Z >= pz
     if size == 1:
         return conv_3d(local, kernel, padding=padding, fill=fill)
-    halo_lo, halo_hi = None, None
-    if pz > 0:
-        halo_lo, halo_hi = _exchange_slices(local[:, :, 0:pz], local[:, :, Z - pz:Z])
-    padded = Tensor(shape=(X + 2 * px, Y + 2 * py, Z + 2 * pz), dtype=local.dtype, val=fill)
-    padded[px:px + X, py:py + Y, pz:pz + Z] = local
-    if halo_lo is not None:
-        padded[px:px + X, py:py + Y, 0:pz] = halo_lo
-    if halo_hi is not None:
-        padded[px:px + X, py:py + Y, pz + Z:pz + Z + pz] = halo_hi
-    return conv_3d(padded.eval(), kernel, padding=0, fill=fill)
+    assert (kx, ky, kz) == (3, 3, 3) and local.dtype in (int, float), "slab convolution runs on the 3x3x3 stencil kernel"
+    lib = _lib()
+    dtype = local.dtype
+    store = _handle(local)
+    plane = X * Y
+    below, above = exchange_halo(store, plane, plane * Z, dtype, fill)
+    ext = lib.store_concat([below, store, above])            # (X, Y, Z + 2), halos in place of z-padding
+    weights = np.ascontiguousarray(kernel.to_numpy()).astype(_NP_OF[dtype]).ravel()
+    out = lib.conv_nd(ext, (X, Y, Z + 2), (3, 3, 3), weights, (px, py, 0),
+                      _abi.value_bits(dtype(fill), _ABI_DTYPE[dtype]))
+    return _adopt(out, (X + 2 * px - 2, Y + 2 * py - 2, Z), dtype)

@@ -16,7 +16,7 @@ import argparse
 ap = argparse.ArgumentParser()
 ap.add_argument("--threads", type=int, default=0)
 ap.add_argument("--cap", type=int, default=0)
-ap.add_argument("--regions", type=int, default=2)
+ap.add_argument("--regions", type=int, default=4, help="park depth")
 ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--build-only", action="store_true")
 ap.add_argument("--no-phase", action="store_true")
@@ -58,7 +58,7 @@ if not args.no_phase:
 ms, ne, ri, ro = lib.profile_read()
 tot = sum(buf)
 names = ["wait for the tile's runs", "views: map + squeeze", "cursor search", "merge (thread 0)",
-         "wait slowest + scan", "look-back + write of the previous tile (2 regions)", "publish + next copies (+ write, 3 regions)", "-"]
+         "wait slowest + scan", "unpark (look-back try + copy)", "publish + park + next copies", "-"]
 print(f"threads {args.threads or A and 128} cap {args.cap or 4096}")
 print(f"merge_eval avg {ms / ne:.3f} ms; runs in {ri // ne} out {ro // ne}; jit launches {lib.jit_launch_count()}")
 for nm, c in zip(names, buf):
