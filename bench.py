@@ -1,21 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- headline measurement of the RLE evaluation hot path on B200.
+"""bench.py -- measurement of the RLE evaluation hot path on B200 (BASELINE.json metric:
+"RLE eval Gruns/s + achieved HBM GB/s; 3^3 voxel conv Gvoxels/s, 1-8 B200").
 
-Workload (BASELINE.json configs[1], "C2"): float32 run-end encoded arrays of 1e9 elements
+Headline line (BASELINE.json configs[1], "C2"): float32 run-end encoded arrays of 1e9 elements
 and 1e7 runs each (4 operands), evaluated through the fused 6-op element-wise DAG
     z = max(a*b + c, d) - abs(a) * 0.5f
 with equal-run compaction, on one GPU.  A "step" is one such evaluation with the operands
 already resident in HBM (`value`), or starting from pinned HOST buffers and ending with the
 result runs back on the host (`e2e`).  Metric: distinct input runs merged per second.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+The same JSON line carries keyed sections for the other configs:
+  "c1"  configs[0]: int32 a + b*c, 1e7 elements / 1e4 runs per operand -- microseconds per eval;
+  "c3"  configs[2]: 3x3x3 convolution of a 512^3 Minecraft-like int32 grid -- Gvoxels/s;
+  "c5"  configs[4] (N > 1): range-sharded array, 1e9 elements / 6.25e7 runs PER RANK (8e9 / 5e8
+        at N = 8): element-wise eval of two co-partitioned operands, sum, max, boundary stitch;
+  "c4"  configs[3] (N > 1): z-slab sharded voxel grid, 2048 x 2048 x 256 PER RANK (2048^3 at
+        N = 8), 3x3x3 convolution with run-encoded halo exchange;
+all through the package's product code (pyskip_b200.functional / pyskip_b200.distributed).
 
-N > 1 (torchrun, one rank per GPU): every rank evaluates its own coordinate-range shard of
-the same size (weak scaling) and the shards are stitched with the fuse_stores boundary rule
-(all-gather of first value / last value / run count; include/pyskip/detail/eval.hpp:581-588).
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--sections c1,c3,c4,c5]
 
 --impl reference times the UNMODIFIED reference (oracle/_ref, built from /root/reference by
-oracle/build_ref.sh) on the host CPUs, on a bounded 1/10 sample of the same workload.
+oracle/build_ref.sh) on the host CPUs on the same configs: C2 at FULL size, under the three
+settings of BASELINE.md section 3 (defaults / one thread / best of accelerated x lazy), plus
+C1 and the 512^3 convolution.
 """
 from __future__ import annotations
 
@@ -31,18 +39,19 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))   # the checker: used by the parity checks and the cpu_baseline legs only
 
 N_ELEMS = 1_000_000_000
 N_RUNS = 10_000_000
 N_OPERANDS = 4
-SAMPLE_DIV = 10          # cpu baseline sample: 1e8 elements / 1e6 runs per operand
+SAMPLE_DIV = 10          # cpu baseline sample inside our arm: 1e8 elements / 1e6 runs per operand
 METRIC = "rle_eval_input_runs_per_s"
 UNIT = "Gruns/s"
 
 
-# ---- synthetic inputs ------------------------------------------------
+# ---- synthetic inputs -----------------------------------------------------
 def gen_operand(seed, n_elems, n_runs):
-    """Run-end arrays: n_runs-1 distinct cut points ~U{1..n-1}; values (1+U{0..63})*0.25f with
+    """C2: n_runs-1 distinct cut points ~U{1..n-1}; values (1+U{0..63})*0.25f with
     v_i != v_{i-1} (canonical), exactly representable so compaction really fires."""
     rng = np.random.default_rng(seed)
     cuts = np.unique(rng.integers(1, n_elems, size=int(n_runs * 1.01) + 16, dtype=np.int64))
@@ -64,6 +73,78 @@ def dag_program(A):
     half = A.value_bits(0.5, A.F32)
     return [(A.OP_SRC, 0), (A.OP_SRC, 1), (F["mul"], 0), (A.OP_SRC, 2), (F["add"], 0), (A.OP_SRC, 3),
             (F["max"], 0), (A.OP_SRC, 0), (F["abs"], 0), (A.OP_CONST, half), (F["mul"], 0), (F["sub"], 0)]
+
+
+def gen_c1(seed=1000, n=10_000_000, r=10_000):
+    """C1: three int32 operands, r runs each over n elements, values U{0..999} canonical."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(3):
+        cuts = np.sort(rng.choice(np.arange(1, n), size=r - 1, replace=False))
+        ends = np.concatenate([cuts, [n]]).astype(np.int32)
+        vals = rng.integers(0, 1000, size=r).astype(np.int32)
+        same = np.nonzero(vals[1:] == vals[:-1])[0] + 1
+        vals[same] = (vals[same] + 1) % 1000
+        out.append((ends, vals))
+    return out
+
+
+def terrain(n=512, seed=3000):
+    """C3: Minecraft-like column data: y is pyskip dim 0 (fastest) so that columns are runs;
+    materials by depth bands plus sparse ores.  Returns numpy [z, x, y] int32."""
+    rng = np.random.default_rng(seed)
+    xs, zs = np.meshgrid(np.arange(n), np.arange(n))
+    h = np.full((n, n), n // 4, dtype=np.float64)
+    for _ in range(4):
+        fx, fz, ph = rng.uniform(0.5, 3.0) / n, rng.uniform(0.5, 3.0) / n, rng.uniform(0, 6.28)
+        h += (n // 10) * 0.25 * np.sin(2 * np.pi * (fx * xs + fz * zs) + ph)
+    h = h.astype(np.int32)
+    y = np.broadcast_to(np.arange(n, dtype=np.int32)[None, None, :], (n, n, n))
+    hh = np.broadcast_to(h[:, :, None], (n, n, n))
+    vol = np.zeros((n, n, n), dtype=np.int32)
+    vol[y < hh] = 1
+    vol[(y < hh) & (y >= hh - 4)] = 3
+    vol[y == hh - 1] = 2
+    vol[y < 2] = 7
+    ore = rng.random((n, n, n)) < 0.004
+    vol[ore & (y < hh - 6) & (y >= 2)] = 14
+    return vol
+
+
+def slab_columns(rank, Y=2048, X=2048, ZL=256, n_ore=8, seed=3000):
+    """C4: the runs of one z-slab of a column-structured terrain WITHOUT materialising voxels.
+    Layout (Y fastest, X, Z): every (x, z) column of Y voxels is bedrock | stone with n_ore
+    single-voxel ores | dirt | grass | air = 2*n_ore + 5 runs (~1 % run density at Y = 2048).
+    Deterministic per global z, so a rank can also produce its neighbours' boundary planes.
+    -> (ends int32 local coordinates, vals int32)."""
+    z0 = rank * ZL
+    xx, zz = np.meshgrid(np.arange(X), np.arange(z0, z0 + ZL))                 # [ZL, X]
+    h = (Y // 4 + (Y // 40) * (np.sin(xx / 97.0) + np.cos(zz / 131.0))).astype(np.int64)
+    ncol = ZL * X
+    rng = np.random.default_rng(seed + 7919 * rank)
+    gaps = rng.integers(2, 50, size=(ncol, n_ore))
+    pos = 2 + np.cumsum(gaps, axis=1)                                          # < 2 + 49*n_ore < h - 6
+    base = (np.arange(ncol, dtype=np.int64) * Y)[:, None]
+    hcol = h.reshape(-1)[:, None]
+    k = 2 * n_ore + 5
+    ends = np.empty((ncol, k), dtype=np.int64)
+    vals = np.empty((ncol, k), dtype=np.int32)
+    ends[:, 0] = 2
+    vals[:, 0] = 7
+    ends[:, 1:1 + 2 * n_ore:2] = pos
+    vals[:, 1:1 + 2 * n_ore:2] = 1
+    ends[:, 2:2 + 2 * n_ore:2] = pos + 1
+    vals[:, 2:2 + 2 * n_ore:2] = 14
+    ends[:, 1 + 2 * n_ore] = (hcol - 4)[:, 0]
+    vals[:, 1 + 2 * n_ore] = 1
+    ends[:, 2 + 2 * n_ore] = (hcol - 1)[:, 0]
+    vals[:, 2 + 2 * n_ore] = 3
+    ends[:, 3 + 2 * n_ore] = hcol[:, 0]
+    vals[:, 3 + 2 * n_ore] = 2
+    ends[:, 4 + 2 * n_ore] = Y
+    vals[:, 4 + 2 * n_ore] = 0
+    ends += base
+    return ends.reshape(-1).astype(np.int32), vals.reshape(-1)
 
 
 # ---- clocks (B200_PROFILING.md recipe) ---------------------------------------------------
@@ -127,62 +208,13 @@ def hbm_peak():
 
 
 def ncu_traffic():
-    """Per-launch DRAM bytes of k_merge_eval from the committed ncu --set full capture."""
+    """Per-launch DRAM bytes of the merge kernel from the committed `ncu --set full` capture
+    (static: measured once per round, not at bench time)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             return json.load(f).get("merge_eval_dram_bytes_per_launch")
     except Exception:
         return None
-
-
-# ---- the reference arm / cpu baseline ----------------------------------------------------
-def reference_step_setup():
-    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
-    import _pyskip_cpp_ext as R           # the unmodified reference, compiled
-    n, r = N_ELEMS // SAMPLE_DIV, N_RUNS // SAMPLE_DIV
-    arrs = []
-    for j in range(N_OPERANDS):
-        ends, vals = gen_operand(2000 + j, n, r)
-        lens = np.diff(np.concatenate([[0], ends.astype(np.int64)]))
-        arrs.append(R.from_numpy(np.repeat(vals, lens)))
-    a, b, c, d = arrs
-
-    def step():
-        z = ((a * b + c).max(d) - a.abs() * 0.5).eval()
-        ends, vals = z.runs()
-        return len(ends)
-
-    return step, N_OPERANDS * r, f"1/{SAMPLE_DIV} of the workload: {n:.0e} elements, {r:.0e} runs per operand"
-
-
-def time_reference(steps, warmup):
-    step, runs_in, sample = reference_step_setup()
-    for _ in range(max(1, warmup)):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = (time.perf_counter() - t0) / steps
-    return runs_in / dt / 1e9, dt * 1e3, sample
-
-
-def run_reference(args, rank):
-    if rank != 0:
-        return
-    try:
-        val, ms, sample = time_reference(args.steps, args.warmup)
-    except Exception as ex:  # oracle/_ref missing
-        print(json.dumps({"impl": "reference", "unavailable": f"{type(ex).__name__}: {ex}"}))
-        return
-    cores = os.cpu_count()
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
 
 
 def workload_config():
@@ -192,6 +224,376 @@ def workload_config():
             "l2": "inputs 320 MB per step > 126 MB L2 (no flush needed)"}
 
 
+# ---- the reference arm / cpu baseline ----------------------------------------------------
+def ref_module():
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    import _pyskip_cpp_ext as R           # the unmodified reference, compiled
+    return R
+
+
+REF_SETTINGS = [
+    ("defaults", {}),
+    ("one_thread", {"parallelize_parts": 1}),
+    ("unaccelerated", {"accelerated_eval": False}),
+    ("lazy", {"flush_tree_size_threshold": 2 ** 30}),
+    ("unaccelerated_lazy", {"accelerated_eval": False, "flush_tree_size_threshold": 2 ** 30}),
+]
+
+
+def ref_apply(R, cfg):
+    """Reset the reference's config map, then set the given keys (pyskip_ext.cpp:29-72)."""
+    R.config.set_all_values({})
+    for key, val in cfg.items():
+        if isinstance(val, bool):
+            R.config.set_bool_value(key, val)
+        else:
+            R.config.set_int_value(key, int(val))
+
+
+def ref_c2_setup(R, div):
+    n, r = N_ELEMS // div, N_RUNS // div
+    arrs = []
+    for j in range(N_OPERANDS):
+        ends, vals = gen_operand(2000 + j, n, r)
+        lens = np.diff(np.concatenate([[0], ends.astype(np.int64)]))
+        dense = np.repeat(vals, lens)
+        arrs.append(R.from_numpy(dense))
+        del dense
+    a, b, c, d = arrs
+
+    def step():
+        z = ((a * b + c).max(d) - a.abs() * 0.5).eval()
+        ends, vals = z.runs()
+        return len(ends)
+
+    return step, N_OPERANDS * r, n, r
+
+
+def time_ref_c2(R, steps, warmup, div, settings):
+    """-> {setting: Gruns/s}, ms per step of the best, sample description, runs out."""
+    step, runs_in, n, r = ref_c2_setup(R, div)
+    res, out_runs = {}, None
+    for name, cfg in settings:
+        ref_apply(R, cfg)
+        for _ in range(max(1, warmup)):
+            out_runs = step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = (time.perf_counter() - t0) / steps
+        res[name] = runs_in / dt / 1e9
+    ref_apply(R, {})
+    sample = (f"full C2: {n:.0e} elements, {r:.0e} runs per operand" if div == 1 else
+              f"1/{div} of C2: {n:.0e} elements, {r:.0e} runs per operand")
+    return res, sample, out_runs
+
+
+def time_ref_c1(R, reps=30):
+    import rle_oracle as O
+    ops = gen_c1()
+    a, b, c = (R.from_numpy(O.to_dense(e, v)) for e, v in ops)
+    ts = []
+    for _ in range(reps + 3):
+        t0 = time.perf_counter()
+        z = (a + b * c).eval()
+        z.runs()
+        ts.append(time.perf_counter() - t0)
+    return float(np.median(ts[3:])) * 1e6
+
+
+def time_ref_c3(R, n, reps=2):
+    """The reference's conv_3d tap loop (src/pyskip/convolve.py:39-59) on an n^3 terrain."""
+    vol = terrain(n)
+    ker = np.random.default_rng(3001).integers(0, 8, size=(3, 3, 3)).astype(np.int32)
+    rt = R.Tensor3i([n, n, n], R.from_numpy(vol.reshape(-1)))
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        s = R.Tensor3i([n + 2] * 3, 0)
+        s[(slice(1, n + 1),) * 3] = rt
+        acc = R.Tensor3i([n, n, n], 0).array()
+        for z in range(3):
+            for y in range(3):
+                for x in range(3):
+                    acc = acc + int(ker[z, y, x]) * s[(slice(x, n + x), slice(y, n + y), slice(z, n + z))].array()
+        acc = acc.eval()
+        ts.append(time.perf_counter() - t0)
+    return float(np.min(ts)), int(len(acc.runs()[0]))
+
+
+def host_mem_gb():
+    try:
+        import psutil
+        return psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        return 0.0
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    try:
+        R = ref_module()
+    except Exception as ex:  # oracle/_ref missing
+        print(json.dumps({"impl": "reference", "unavailable": f"{type(ex).__name__}: {ex}"}))
+        return
+    # full-size C2 needs ~4 GB per dense operand while it is being encoded (+ 0.5 GB of stores)
+    div = 1 if host_mem_gb() > 48 else SAMPLE_DIV
+    steps = max(1, min(args.steps, 5 if div == 1 else 20))
+    try:
+        res, sample, out_runs = time_ref_c2(R, steps, min(args.warmup, 1), div, REF_SETTINGS)
+    except MemoryError:
+        div = SAMPLE_DIV
+        res, sample, out_runs = time_ref_c2(R, min(args.steps, 20), 1, div, REF_SETTINGS)
+    best = max(res, key=res.get)
+    val = res[best]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": N_OPERANDS * (N_RUNS // div) / val / 1e6,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload_config(), reference_sample=sample, reference_setting=best),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample,
+                         "settings": res, "best_setting": best, "runs_out": out_runs},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    sections = (args.sections or "c1,c3").split(",")
+    if "c1" in sections:
+        try:
+            line["c1"] = {"us_per_eval": time_ref_c1(R), "cores": cores,
+                          "workload": "C1: int32 a + b*c, 1e7 elements / 1e4 runs per operand"}
+        except Exception as ex:
+            line["c1"] = {"error": f"{type(ex).__name__}: {ex}"}
+    if "c3" in sections:
+        try:
+            n = 512 if host_mem_gb() > 16 else 256
+            dt, r_out = time_ref_c3(R, n)
+            line["c3"] = {"ms_per_conv": dt * 1e3, "gvoxels_per_s": n ** 3 / dt / 1e9, "grid": [n, n, n],
+                          "runs_out": r_out, "cores": cores,
+                          "workload": f"C3: 3x3x3 conv of a {n}^3 int32 terrain, padding 1 (reference tap loop, defaults)"}
+        except Exception as ex:
+            line["c3"] = {"error": f"{type(ex).__name__}: {ex}"}
+    print(json.dumps(line))
+
+
+# ---- our arm: sections ---------------------------------------------------------------------
+def section_c1(lib, A):
+    """configs[0]: latency of one evaluation, operands resident, run count back on the host."""
+    import rle_oracle as O
+    ops = gen_c1()
+    stores = [lib.store_from_runs(e, v) for e, v in ops]
+    I = A.OP_I
+    prog = [(A.OP_SRC, 0), (A.OP_SRC, 1), (A.OP_SRC, 2), (I["mul"], 0), (I["add"], 0)]
+    run = lib.prepare_eval([(s, []) for s in stores], prog, A.I32)
+    for _ in range(10):
+        res = run()
+    ts = []
+    for _ in range(300):
+        t0 = time.perf_counter()
+        res = run()
+        ts.append(time.perf_counter() - t0)
+    got = res.runs()
+    want = O.eval_sources([(e, v, []) for e, v in ops], lambda a, b, c: O.add(a, O.mul(b, c)))
+    ok = bool(np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]))
+    us = float(np.median(ts)) * 1e6
+    return {"workload": "C1: int32 a + b*c, 1e7 elements / 1e4 runs per operand (3e4 input runs)",
+            "us_per_eval": us, "us_p10": float(np.percentile(ts, 10)) * 1e6, "runs_out": int(res.nruns),
+            "gruns_per_s": 3e4 / us / 1e3, "checks": "ok (bit-exact vs oracle)" if ok else "MISMATCH"}
+
+
+def section_c3(lib, A, n=512, reps=7):
+    """configs[2]: 3x3x3 convolution of an n^3 terrain through pyskip_b200.functional.conv_3d."""
+    import pyskip_b200 as ps
+    from pyskip_b200 import _pyskip_b200_ext as E
+    import rle_oracle as O
+    vol = terrain(n)
+    ker = np.random.default_rng(3001).integers(0, 8, size=(3, 3, 3)).astype(np.int32)
+    t = ps.Tensor.from_numpy(vol).eval()
+    k = ps.Tensor.from_numpy(ker)
+    r_in = t.rle_length()
+    for _ in range(3):
+        out = ps.functional.conv_3d(t, k, padding=1)
+    r_out = out.rle_length()
+    E.synchronize()
+    lib.profile(True)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = ps.functional.conv_3d(t, k, padding=1)
+        E.synchronize()
+        times.append(time.perf_counter() - t0)
+    kms, nev, _, _ = lib.profile_read()
+    lib.profile(False)
+    dt = float(np.median(times))
+    # piecewise exact check against the dense oracle (input slab + 1-voxel halo), SURVEY 8c
+    got = out.to_numpy()
+    ok = True
+    for z0, z1 in ((0, 3), (n // 2, n // 2 + 2), (n - 3, n)):
+        lo, hi = max(0, z0 - 1), min(n, z1 + 1)
+        sub = O.conv3d_dense(vol[lo:hi], ker, padding=1, fill=0)[z0 - lo:z0 - lo + (z1 - z0)]
+        ok = ok and bool(np.array_equal(got[z0:z1], sub))
+    peak, _ = hbm_peak()
+    alg = 8.0 * (r_in + r_out)
+    kernel_ms = kms / max(1, nev)
+    sec = {"workload": f"C3: 3x3x3 conv of a {n}^3 Minecraft-like int32 grid, padding 1, fill 0",
+           "grid": [n, n, n], "runs_in": int(r_in), "run_density": r_in / vol.size, "runs_out": int(r_out),
+           "ms_per_conv": dt * 1e3, "gvoxels_per_s": vol.size / dt / 1e9,
+           "kernel": "k_conv_rows (stencil over runs)", "kernel_ms": kernel_ms,
+           "roofline": {"bound": "hbm", "algorithmic_bytes": alg, "achieved": alg / (kernel_ms * 1e-3) / 1e9 if kernel_ms else None,
+                        "peak": peak, "unit": "GB/s",
+                        "frac": (alg / (kernel_ms * 1e-3) / 1e9 / peak) if kernel_ms else None,
+                        "note": "algorithmic bytes = 8 B x (input runs + output runs): every row is read by "
+                                "27 taps but counted once (SURVEY 8d)"},
+           "checks": "ok (dense oracle on 3 z-slabs, bit-exact)" if ok else "MISMATCH"}
+    try:
+        R = ref_module()
+        m = 128
+        dt2, _ = time_ref_c3(R, m, reps=1)
+        sec["cpu_baseline"] = {"gvoxels_per_s": m ** 3 / dt2 / 1e9, "grid": [m, m, m], "cores": os.cpu_count(),
+                               "kind": "reference", "sample": f"{m}^3 terrain (the 512^3 run is in --impl reference)"}
+    except Exception as ex:
+        sec["cpu_baseline"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
+    return sec
+
+
+def section_c5(world, rank, dist, torch, n_local=1_000_000_000, r_local=62_500_000):
+    """configs[4]: range-sharded array (local int32 coordinates + int64 rank offset): eval of two
+    co-partitioned operands, sum / max all-reduce, boundary stitching; product code
+    pyskip_b200.distributed."""
+    import pyskip_b200 as ps
+    from pyskip_b200 import _pyskip_b200_ext as E, distributed as D
+    import rle_oracle as O
+    span = n_local * world
+
+    def shard(shift):
+        g = np.random.default_rng(5000 + rank + 100 * shift)
+        lens = g.geometric(1.0 / (n_local / r_local), size=int(r_local * 1.02))
+        ends = np.cumsum(lens, dtype=np.int64)
+        ends = ends[ends < n_local]
+        ends = np.concatenate([ends, [n_local]]).astype(np.int32)
+        vals = g.integers(-1000, 1001, size=len(ends)).astype(np.int32)
+        vals[0] = 7 + shift             # every shard starts and ends with the same value:
+        vals[-1] = 7 + shift            # all N-1 boundaries must stitch
+        return ends, vals
+
+    (ea, va), (eb, vb) = shard(0), shard(1)
+    A_ = D.ShardedTensor(ps.Tensor(shape=(n_local,), val=E.IntArray._from_runs(ea, va)), span)
+    B_ = D.ShardedTensor(ps.Tensor(shape=(n_local,), val=E.IntArray._from_runs(eb, vb)), span)
+    (A_.local + B_.local).eval()                       # warm-up: compiles the specialised kernel
+
+    def sync():
+        E.synchronize()
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    reps = 3
+    t_eval, t_rest = [], []
+    for _ in range(reps):
+        sync()
+        t0 = time.perf_counter()
+        C_ = D.ShardedTensor(A_.map(lambda a, b: a + b, B_).local.eval(), span)
+        E.synchronize()
+        t1 = time.perf_counter()
+        keep, first, total = C_.stitch(bitwise=False)  # already evaluated under bitwise equality
+        s, mx = C_.sum(), C_.max()
+        sync()
+        t2 = time.perf_counter()
+        t_eval.append(t1 - t0)
+        t_rest.append(t2 - t1)
+    # checks: (i) run-for-run oracle on the first 2e6 coordinates of this shard, (ii) global sum
+    # in closed form (sum(a) + sum(b) mod 2^32), (iii) every boundary stitches: total = sum - (N-1)
+    cut = 2_000_000
+    ia, ib = int(np.searchsorted(ea, cut)) + 1, int(np.searchsorted(eb, cut)) + 1
+    pa = (np.minimum(ea[:ia], cut), va[:ia])
+    pb = (np.minimum(eb[:ib], cut), vb[:ib])
+    we, wv = O.eval_sources([(pa[0], pa[1], []), (pb[0], pb[1], [])], lambda a, b: O.add(a, b))
+    le, lv = C_.local[0:cut].eval().to_runs()
+    ok = bool(np.array_equal(np.asarray(le), we) and np.array_equal(np.asarray(lv), wv))
+    la = np.diff(np.concatenate([[0], ea.astype(np.int64)]))
+    lb = np.diff(np.concatenate([[0], eb.astype(np.int64)]))
+    local_sum = (int(np.dot(la, va.astype(np.int64))) + int(np.dot(lb, vb.astype(np.int64)))) & 0xFFFFFFFF
+    stat = torch.tensor([local_sum, C_.local.rle_length()], dtype=torch.int64, device="cuda")
+    alls = [torch.zeros_like(stat) for _ in range(world)]
+    dist.all_gather(alls, stat)
+    alls = torch.stack(alls).cpu().numpy()
+    want_sum = int(alls[:, 0].sum()) & 0xFFFFFFFF
+    want_sum = want_sum - (1 << 32) if want_sum >= (1 << 31) else want_sum
+    ok = ok and s == want_sum and total == int(alls[:, 1].sum()) - (world - 1)
+    okt = torch.tensor([1 if ok else 0], dtype=torch.int64, device="cuda")
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    dte = torch.tensor([min(t_eval), min(t_rest)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(dte, op=dist.ReduceOp.MAX)
+    ev, rest = float(dte[0]), float(dte[1])
+    runs_in = 2 * r_local * world
+    return {"workload": f"C5: {span:.1e} elements / {runs_in // 2:.2e} runs per operand range-sharded over {world} GPUs "
+                        "(local int32 coordinates + int64 rank offset): a + b, boundary stitch, sum, max",
+            "eval_ms": ev * 1e3, "stitch_sum_max_ms": rest * 1e3, "gruns_per_s_eval": runs_in / ev / 1e9,
+            "gruns_per_s_all": runs_in / (ev + rest) / 1e9, "global_output_runs": int(total),
+            "sum": int(s), "max": int(mx),
+            "checks": "ok (oracle prefix per rank, closed-form sum, all boundaries stitched)" if int(okt) else "MISMATCH"}
+
+
+def section_c4(world, rank, dist, torch, Y=2048, X=2048, ZL=256):
+    """configs[3]: z-slab per rank, 3x3x3 convolution with halo exchange (as runs, exact sizes,
+    device to device); product code pyskip_b200.distributed.conv_3d_slab."""
+    import pyskip_b200 as ps
+    from pyskip_b200 import _pyskip_b200_ext as E, distributed as D
+    import rle_oracle as O
+    ends, vals = slab_columns(rank, Y, X, ZL)
+    t = ps.Tensor(shape=(Y, X, ZL), val=E.IntArray._from_runs(ends, vals))
+    ker = np.random.default_rng(3001).integers(0, 8, size=(3, 3, 3)).astype(np.int32)
+    k = ps.Tensor.from_numpy(ker)
+
+    def sync():
+        E.synchronize()
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    out = D.conv_3d_slab(t, k, padding=1, fill=0)      # warm-up
+    ts = []
+    for _ in range(3):
+        sync()
+        t0 = time.perf_counter()
+        out = D.conv_3d_slab(t, k, padding=1, fill=0)
+        E.synchronize()
+        sync()
+        ts.append(time.perf_counter() - t0)
+    # piecewise parity (SURVEY 8c): first, middle and last z-plane of the slab against the dense
+    # oracle; the neighbours' boundary planes come from the same deterministic generator
+    plane = Y * X
+
+    def planes(r, z_lo, z_hi):
+        if r < 0 or r >= world:
+            return np.zeros((z_hi - z_lo, X, Y), np.int32)
+        e, v = (ends, vals) if r == rank else slab_columns(r, Y, X, ZL)
+        i0 = int(np.searchsorted(e, z_lo * plane, side="right"))
+        i1 = int(np.searchsorted(e, z_hi * plane - 1, side="right"))
+        ee = np.minimum(e[i0:i1 + 1].astype(np.int64), z_hi * plane) - z_lo * plane
+        return O.to_dense(ee.astype(np.int32), v[i0:i1 + 1]).reshape(z_hi - z_lo, X, Y)
+
+    ok = True
+    for z in (0, ZL // 2, ZL - 1):
+        below = planes(rank - 1, ZL - 1, ZL) if z == 0 else planes(rank, z - 1, z)
+        above = planes(rank + 1, 0, 1) if z == ZL - 1 else planes(rank, z + 1, z + 2)
+        ext = np.concatenate([below, planes(rank, z, z + 1), above])
+        want = O.conv3d_dense(ext, ker, padding=1, fill=0)[1]
+        got = out[:, :, z:z + 1].to_numpy().reshape(X, Y)
+        ok = ok and bool(np.array_equal(got, want))
+    stat = torch.tensor([t.rle_length(), out.rle_length(), 1 if ok else 0], dtype=torch.int64, device="cuda")
+    mn = stat.clone()
+    dist.all_reduce(stat)
+    dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+    dt = torch.tensor([min(ts)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt)
+    vox = Y * X * ZL * world
+    return {"workload": f"C4: {Y} x {X} x {ZL * world} int32 voxel grid, z-slab of {ZL} planes per rank, "
+                        "3x3x3 conv, halo exchange as runs (exact sizes, device to device)",
+            "grid": [Y, X, ZL * world], "voxels": vox, "input_runs": int(stat[0]), "output_runs": int(stat[1]),
+            "conv_ms": dt * 1e3, "gvoxels_per_s": vox / dt / 1e9,
+            "checks": "ok (dense oracle on first / middle / last plane of every slab, bit-exact)" if int(mn[2]) else "MISMATCH"}
+
+
 # ---- our arm -----------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -199,7 +601,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only)")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the C2 workload (debug only)")
+    ap.add_argument("--sections", default=None, help="comma list of c1,c3,c4,c5 (default: all that apply)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -210,7 +613,7 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     import torch
-    from pyskip_b200 import _abi as A
+    from pyskip_b200 import _abi as A, _pyskip_b200_ext as E, distributed as D
     lib = A.lib()
     assert not lib.is_simulator()
     torch.cuda.set_device(local_rank)
@@ -219,6 +622,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        D.use_torch_stream()              # library kernels and NCCL collectives on one stream
+    sections = args.sections.split(",") if args.sections is not None else (
+        ["c1", "c3"] if world == 1 else ["c5", "c4"])
 
     n_elems = int(N_ELEMS * args.scale)
     n_runs = int(N_RUNS * args.scale)
@@ -235,51 +641,13 @@ def main():
     out_v = torch.empty(N_OPERANDS * n_runs, dtype=torch.float32, pin_memory=True)
     prog = dag_program(A)
 
-    def upload():
-        return [lib.store_from_runs(pe.numpy(), pv.numpy()) for pe, pv in host]
-
-    STITCH_BATCH = 32
-    pending = [0]      # triples written on the device and not exchanged yet
-    last_total = [None]
-
-    def stitch(res, step):
-        """fuse_stores boundary rule across ranks (eval.hpp:581-588): every rank contributes
-        (first value, last value, run count) of its shard; a rank drops its last run when the
-        next rank starts with an equal value, an exclusive scan of the counts gives global run
-        offsets.  Each step appends its triple to a device buffer (one tiny library kernel, no
-        host synchronisation); the ranks exchange the pending triples with ONE all-gather every
-        STITCH_BATCH steps and at the end of the region -- the collective is latency-bound
-        (24 bytes per rank and step), so it is batched rather than issued per step."""
-        if dist is None:
-            return
-        lib.store_boundary_device(res, st_mine.data_ptr() + 24 * pending[0])
-        pending[0] += 1
-        if pending[0] == STITCH_BATCH:
-            stitch_drain()
-
-    def stitch_drain():
-        """Exchange the pending triples; -> global run count of the last step."""
-        if dist is None or pending[0] == 0:
-            return last_total[0]
-        n = pending[0]
-        lib.synchronize()                              # the triples are written
-        dist.all_gather_into_tensor(st_all[:world * n * 3], st_mine[:n * 3])
-        allv = st_all[:world * n * 3].view(world, n, 3).cpu()
-        counts = allv[:, n - 1, 2].clone()
-        for r in range(world - 1):
-            if allv[r, n - 1, 1] == allv[r + 1, n - 1, 0]:
-                counts[r] -= 1
-        pending[0] = 0
-        last_total[0] = int(counts.sum())
-        return last_total[0]
-
-    if dist is not None:
-        st_mine = torch.zeros(STITCH_BATCH * 3, dtype=torch.int64, device="cuda")
-        st_all = torch.zeros(world * STITCH_BATCH * 3, dtype=torch.int64, device="cuda")
-    resident = upload()
+    # weak scaling (N > 1): every rank evaluates its own shard; the shards are stitched with the
+    # fuse_stores boundary rule through the package's BoundaryStitcher (device-side triples, one
+    # all-gather per 32 steps and at the end of the timed region)
+    stitcher = D.BoundaryStitcher(batch=32) if dist is not None else None
+    resident = [lib.store_from_runs(pe.numpy(), pv.numpy()) for pe, pv in host]
     srcs = [(s, []) for s in resident]
 
-    step_no = [0]
     # The resident step goes through psk_eval_async: the kernels are queued and the call
     # returns; a result's run count is read two steps later, so the host work of step i+1
     # (plan, launches) overlaps the kernels of step i.  Every result is completed and checked
@@ -296,8 +664,8 @@ def main():
 
     def step_resident():
         res = eval_resident()
-        stitch(res, step_no[0])
-        step_no[0] += 1
+        if stitcher is not None:
+            stitcher.add(res)
         inflight.append(res)
         while len(inflight) > 2:
             complete(inflight.pop(0))
@@ -318,7 +686,8 @@ def main():
     drain_resident()
     runs_out = res.nruns
     del res
-    stitch_drain()
+    if stitcher is not None:
+        stitcher.drain()
 
     # ---- timed region: K resident steps, device events on the library stream -------------
     sampler = ClockSampler(local_rank)
@@ -332,7 +701,8 @@ def main():
     for _ in range(args.steps):
         step_resident()
     drain_resident()                      # every step's result is complete and checked ...
-    total_out = stitch_drain()            # ... and every step's exchange has completed inside the region
+    if stitcher is not None:
+        stitcher.drain()                  # ... and every step's exchange has completed inside the region
     ms_total = lib.timer_stop()
     barrier()
     t1 = time.time()
@@ -362,21 +732,19 @@ def main():
 
     def run_e2e(n):
         pending = upload_async()
-        prev = None
+        keep = None
         n_out = 0
-        verbose = os.environ.get("BENCH_E2E_VERBOSE") == "1"
         for i in range(n):
-            if verbose:
-                print(f"e2e step {i} starts at {time.perf_counter() * 1e3:.2f} ms", file=sys.stderr)
             nxt = upload_async() if i + 1 < n else None
             r = lib.eval([(s, []) for s in pending], prog, A.F32, A.EQ_BITWISE)
             n_out = r.nruns
             oe, ov = outs[i & 1]
             lib.store_runs_async(r, oe.numpy(), ov.numpy())
-            prev = (r, pending)          # keep alive until their copies have been ordered
+            keep = (r, pending)          # keep alive until their copies have been ordered
             pending = nxt
         lib.copy_synchronize()
         lib.synchronize()
+        del keep
         return n_out
 
     n_e2e = max(4, min(args.steps, 12))
@@ -391,32 +759,49 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_val = world * runs_in_step / e2e_s / 1e9
+    del resident, srcs, eval_resident
+
+    # ---- the other configs ------------------------------------------------------------------
+    extra = {}
+    if world == 1:
+        if "c1" in sections:
+            extra["c1"] = section_c1(lib, A)
+        if "c3" in sections:
+            extra["c3"] = section_c3(lib, A)
+    else:
+        if "c5" in sections:
+            extra["c5"] = section_c5(world, rank, dist, torch)
+        if "c4" in sections:
+            extra["c4"] = section_c4(world, rank, dist, torch)
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (k_merge_eval) -----------------------------------
+    # ---- roofline of the dominant kernel (the merge kernel) --------------------------------
     peak, peak_src = hbm_peak()
     avg_merge_ms = merge_ms / max(1, n_eval)
     alg_bytes = 8.0 * (runs_in_step + runs_out)      # (4 B end + 4 B value) per run read / written
     achieved = alg_bytes / (avg_merge_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(), "kernel": "k_merge_eval", "kernel_ms": avg_merge_ms,
+                "traffic": ncu_traffic(), "traffic_source": "static: profiles/traffic.json (ncu --set full, this round)",
+                "kernel": "psk_jit_merge_eval (k_merge_eval specialised by NVRTC)", "kernel_ms": avg_merge_ms,
                 "kernel_share_of_step": avg_merge_ms / ms_step, "algorithmic_bytes": alg_bytes,
-                "peak_source": peak_src}
+                "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0}
 
-    # ---- cpu baseline: the reference itself on the host cores, bounded sample -------------
+    # ---- cpu baseline: the reference itself on the host cores, bounded sample ---------------
     try:
-        cpu_val, cpu_ms, sample = time_reference(steps=3, warmup=1)
-        cpu = {"value": cpu_val, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": sample,
-               "ms_per_sample_step": cpu_ms}
+        R = ref_module()
+        res, sample, _ = time_ref_c2(R, steps=3, warmup=1, div=SAMPLE_DIV, settings=REF_SETTINGS[:3])
+        best = max(res, key=res.get)
+        cpu = {"value": res[best], "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": sample,
+               "settings": res, "best_setting": best}
     except Exception as ex:
         cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                "sample": f"unavailable: {type(ex).__name__}: {ex}"}
 
-    print(json.dumps({
+    line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
@@ -425,7 +810,9 @@ def main():
         "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
                 "h2d_bytes_per_step": 8 * runs_in_step, "d2h_bytes_per_step": 8 * int(n_out)},
         "gpu_launches": int(launches), "clocks": clocks,
-    }))
+    }
+    line.update(extra)
+    print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 

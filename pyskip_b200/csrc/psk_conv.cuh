@@ -102,17 +102,23 @@ struct ConvRow {
     }
   }
 
-  // the stream's next piece (its current one ends at head[s])
-  PSK_D void advance(const ConvParams& p, int s) {
-    const int r = s / KW, a = s % KW;
-    const int32_t shift = p.px - a;
-    if (head[s] == p.W + shift) {  // the row is finished: right padding
-      val[s] = p.fill;
-      head[s] = kSentinel;
-    } else {
-      const int2 run = ld_nc(p.runs + (++cur[s]));
-      val[s] = (uint32_t)run.y;
-      head[s] = imin(run.x - rowbase[r], p.W) + shift;
+  // Streams whose current piece ends at e move on to their next piece.  Straight-line and
+  // predicated: the lanes of a warp (different rows) advance different streams at every step,
+  // so a branch per stream would execute nearly all of them serially, each with its own
+  // dependent load; here the loads of all streams are issued back to back.
+  PSK_D void advance_all(const ConvParams& p, int32_t e) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const int r = s / KW, a = s % KW;
+      const int32_t shift = p.px - a;
+      const bool adv = head[s] == e;
+      const bool fin = adv && e == p.W + shift;  // the row is finished: right padding
+      const bool ld = adv && !fin;
+      int2 run = make_int2(0, 0);
+      if (ld) run = ld_nc(p.runs + cur[s] + 1);
+      cur[s] += ld ? 1 : 0;
+      val[s] = fin ? p.fill : (ld ? (uint32_t)run.y : val[s]);
+      head[s] = fin ? kSentinel : (ld ? imin(run.x - rowbase[r], p.W) + shift : head[s]);
     }
   }
 
@@ -130,11 +136,13 @@ struct ConvRow {
     return acc;
   }
 
-  // Sweep one output row.  WRITE = false: count the spans kept before the row's last span;
-  // WRITE = true: store them at dst.  Returns the count; *fv / *lv = value of the first /
-  // last span of the row.
+  // Sweep one output row.  WRITE = false: count the spans kept before the row's last span (the
+  // first `stage_cap` of them are also parked at stage[j * stage_stride], so that rows with
+  // few spans -- nearly all of them -- need no second sweep); WRITE = true: store them at dst.
+  // Returns the count; *fv / *lv = value of the first / last span of the row.
   template <bool WRITE>
-  PSK_D int32_t sweep(const ConvParams& p, int32_t y, int32_t z, int2* dst, uint32_t* fv, uint32_t* lv) {
+  PSK_D int32_t sweep(const ConvParams& p, int32_t y, int32_t z, int2* dst, uint32_t* fv, uint32_t* lv,
+                      int2* stage = nullptr, int stage_cap = 0, int stage_stride = 1) {
     init(p, y, z);
     const int32_t rowflat = (z * p.OH + y) * p.OW;
     const bool typed = p.typed_float != 0;
@@ -151,15 +159,14 @@ struct ConvRow {
         *fv = v;
       } else if (!payload_equal(pv, v, typed)) {
         if (WRITE) dst[n] = make_int2(rowflat + pe, (int32_t)pv);
+        else if (n < stage_cap) stage[n * stage_stride] = make_int2(rowflat + pe, (int32_t)pv);
         ++n;
       }
       pe = e;
       pv = v;
       have = true;
       if (e >= p.OW) break;
-#pragma unroll
-      for (int s = 0; s < NS; ++s)
-        if (head[s] == e) advance(p, s);
+      advance_all(p, e);
     }
     *lv = pv;
     return n;
@@ -175,6 +182,10 @@ struct ConvRow {
 template <int KW, int KH, int KD, bool IS_F>
 __global__ void __launch_bounds__(kConvRowThreads) k_conv_rows(ConvParams p) {
   constexpr int T = kConvRowThreads;
+  // spans of the rows of this tile, parked during the counting sweep: span j of thread t at
+  // [j * T + t] (conflict-free for 8-byte accesses)
+  constexpr int kStage = 40;
+  __shared__ int2 s_stage[kStage * T];
   __shared__ uint32_t s_fv[T + 1];
   __shared__ int32_t s_warp[T / 32 + 2];
   __shared__ int32_t s_lbsum[LookW<T>::value * (T / 32)];
@@ -194,7 +205,7 @@ __global__ void __launch_bounds__(kConvRowThreads) k_conv_rows(ConvParams p) {
   ConvRow<KW, KH, KD, IS_F> cr;
   uint32_t fv = 0, lv = 0;
   int32_t cnt = 0;
-  if (active) cnt = cr.template sweep<false>(p, y, z, nullptr, &fv, &lv);
+  if (active) cnt = cr.template sweep<false>(p, y, z, nullptr, &fv, &lv, s_stage + tid, kStage, T);
   s_fv[tid] = fv;
   if (tid == T - 1) {  // first value of the row behind the tile
     const int32_t nrow = tile * T + T;
@@ -222,7 +233,11 @@ __global__ void __launch_bounds__(kConvRowThreads) k_conv_rows(ConvParams p) {
   }
   if (active) {
     int2* const dst = p.out + gofs + ofs;
-    cr.template sweep<true>(p, y, z, dst, &fv, &lv);
+    if (cnt <= kStage) {
+      for (int32_t j = 0; j < cnt; ++j) dst[j] = s_stage[j * T + tid];
+    } else {
+      cr.template sweep<true>(p, y, z, dst, &fv, &lv);  // a row with many spans: sweep it again
+    }
     if (keep_last) dst[cnt] = make_int2((z * p.OH + y) * p.OW + p.OW, (int32_t)lv);
   }
 }

@@ -48,6 +48,8 @@ namespace psk {
 constexpr int kTileThreads = PSK_TILE_THREADS;
 constexpr int kTileCap = PSK_TILE_CAP;  // in-tile runs of all sources together
 constexpr int kSentinel = 0x7fffffff;
+// Look-back chain word: (status << 32) | count.
+enum { ST_INVALID = 0, ST_AGGREGATE = 1, ST_PREFIX = 2 };
 constexpr int kStateStride = 4;  // 64-bit words per look-back entry (one 32-byte sector per tile)
 // per source beyond its in-tile runs: two look-ahead runs + up to two pairs of 16-byte alignment
 constexpr int kTileSlack = 4 * PSK_MAX_SOURCES;
@@ -158,6 +160,7 @@ PSK_D int32_t warp_count_samples(const DSource& s, int32_t ns, int32_t S, int32_
   return lo + __popc(__ballot_sync(0xffffffffu, before));
 }
 
+#ifndef __CUDACC_RTC__  // (the run-time specialisation compiles the merge kernel only)
 // ---------------------------------------------------------------------------------------
 // k_prepare: one warp per source.  [a, e) = runs whose mapped end is in (0, span], cut
 // after the first run that reaches span (everything later is a zero-length mapped run).
@@ -210,8 +213,6 @@ PSK_D int sample_owner(const int32_t* s_off, int k, int32_t sid) {
   return l;
 }
 
-// Look-back chain word: (status << 32) | count.
-enum { ST_INVALID = 0, ST_AGGREGATE = 1, ST_PREFIX = 2 };
 
 // ---------------------------------------------------------------------------------------
 // k_partition: samples -> merged ranks -> tile bounds, in one kernel.
@@ -422,6 +423,8 @@ __global__ void __launch_bounds__(kPartBlock) k_partition(DPlan* p) {
   }
 }
 
+#endif  // !__CUDACC_RTC__
+
 // ---------------------------------------------------------------------------------------
 // Block-wide exclusive scan of one int per thread (warp shuffles + one shared hop).
 template <int T>
@@ -527,14 +530,19 @@ PSK_D int32_t lookback_finish(unsigned long long* state, int32_t tile, int32_t c
         }
       }
       __syncthreads();
-      // fold in tile order (window, then warp): stop behind the first piece with a PREFIX
+      // fold in tile order (window, then warp), lane q takes piece q: stop behind the first
+      // piece with a PREFIX
       bool done = false;
+      for (int q0 = 0; q0 < kLookW * NW && !done; q0 += 32) {
+        const int q = q0 + lane;
+        const bool in = q < kLookW * NW;
+        const unsigned pm = __ballot_sync(0xffffffffu, in && s_has[q] != 0);
+        const int first = pm ? (__ffs((int)pm) - 1) : 32;
+        int32_t c = (in && lane <= first) ? s_sum[q] : 0;
 #pragma unroll
-      for (int q = 0; q < kLookW * NW; ++q) {
-        if (!done) {
-          excl += s_sum[q];
-          done = s_has[q] != 0;
-        }
+        for (int dd = 16; dd > 0; dd >>= 1) c += __shfl_xor_sync(0xffffffffu, c, dd);
+        excl += c;
+        done = pm != 0;
       }
       if (done) break;
     }
@@ -577,15 +585,20 @@ PSK_D bool lookback_try(unsigned long long* state, int32_t tile, int32_t count, 
       }
     }
     __syncthreads();
+    // fold in tile order (window, then warp), lane q takes piece q
     bool done = false;
+    for (int q0 = 0; q0 < kLookW * NW && !done; q0 += 32) {
+      const int q = q0 + lane;
+      const bool in = q < kLookW * NW;
+      const int32_t h = in ? s_has[q] : 0;
+      const unsigned pm = __ballot_sync(0xffffffffu, (h & 1) != 0);
+      const int first = pm ? (__ffs((int)pm) - 1) : 32;
+      if (__ballot_sync(0xffffffffu, (h & 2) != 0 && lane <= first)) ok = false;
+      int32_t c = (in && lane <= first) ? s_sum[q] : 0;
 #pragma unroll
-    for (int q = 0; q < kLookW * NW; ++q) {
-      if (!done) {
-        const int32_t h = s_has[q];
-        excl += s_sum[q];
-        if (h & 2) ok = false;
-        done = (h & 1) != 0;
-      }
+      for (int dd = 16; dd > 0; dd >>= 1) c += __shfl_xor_sync(0xffffffffu, c, dd);
+      excl += c;
+      done = pm != 0;
     }
     if (!done) ok = false;
   }
@@ -756,6 +769,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
   __shared__ int32_t s_lbsum[LookW<T>::value * (T / 32)];
   __shared__ int32_t s_lbhas[LookW<T>::value * (T / 32)];
   __shared__ int32_t s_newstart[PSK_MAX_SOURCES];
+  __shared__ int32_t s_coarse[K * (T / 8 + 1)];  // cursors of every 8th thread
   __shared__ psk_mbar_t s_bar;
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -969,15 +983,42 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     const int32_t c0 = lo + (int32_t)((width * tid) / T);
     const int32_t c1 = lo + (int32_t)((width * (tid + 1)) / T);
 
-    // first staged run of every source whose end is > c0: branch-free binary searches that
-    // advance in lock step over the sources (the look-ahead run bounds each of them)
+    // first staged run of every source whose end is > c0.  Two levels: the cursors of every
+    // 8th thread are found first -- k * T/8 full binary searches spread over the threads, one
+    // each -- and bracket the searches of the threads in between (branch-free, in lock step
+    // over the sources; the look-ahead run bounds each of them).
     int32_t cur[K], head[K], rem[K];
     uint32_t val[K];
     int32_t base = 0;
+    constexpr int CG = 8, NC = T / CG;
+    if (!fail) {
+      for (int32_t q = tid; q < NC * k; q += T) {
+        const int i = q / NC, g_ = q - i * NC;
+        const int32_t cg = lo + (int32_t)((width * (g_ * CG)) / T);
+        // candidates: the in-tile runs and BOTH look-ahead runs -- the first one may end exactly at
+        // the tile's upper bound (a tie with the splitter), which is not beyond c0 in an empty
+        // tile (lo == hi); the second one always is
+        int32_t c = RD + lay.start[i], r = lay.len[i] + 2;
+        while (r > 1) {
+          const int32_t half = r >> 1;
+          c += (sm.ldx(c + half - 1) <= cg) ? half : 0;
+          r -= half;
+        }
+        s_coarse[i * (NC + 1) + g_] = c;
+        if (g_ == 0) s_coarse[i * (NC + 1) + NC] = RD + lay.start[i] + lay.len[i] + 1;
+      }
+    }
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < K; ++i) {
-      cur[i] = (i < k) ? RD + lay.start[i] : 0;
-      rem[i] = (i < k && !fail) ? lay.len[i] + 1 : 1;
+      if (i < k && !fail) {
+        const int32_t a0 = s_coarse[i * (NC + 1) + tid / CG], a1 = s_coarse[i * (NC + 1) + tid / CG + 1];
+        cur[i] = a0;
+        rem[i] = a1 - a0 + 1;
+      } else {
+        cur[i] = 0;
+        rem[i] = 1;
+      }
     }
     {
       int32_t longest = 1;
@@ -1094,6 +1135,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
   PSK_PHASE_FLUSH;
 }
 
+#ifndef __CUDACC_RTC__
 template <int K>
 __global__ void __launch_bounds__(kTileThreads, kCtasPerSm) k_merge_eval_interp(DPlan* p) {
   __shared__ psk_node s_prog[PSK_MAX_PROGRAM];
@@ -1103,5 +1145,7 @@ __global__ void __launch_bounds__(kTileThreads, kCtasPerSm) k_merge_eval_interp(
   if (p->eq != 0) merge_eval_tile_loop<K, true, -1>(p, ev);
   else merge_eval_tile_loop<K, false, -1>(p, ev);
 }
+
+#endif  // !__CUDACC_RTC__
 
 }  // namespace psk

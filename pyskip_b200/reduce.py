@@ -48,7 +48,12 @@ def _axis0(t, kind, keepdims):
 
 
 def _builtin(t, kind, axis, keepdims, op):
-    if axis == 0:
+    # The reference's tree reduces an axis of an N-D tensor correctly only when its extent is a
+    # power of two (an odd extent recurses WITHOUT the axis, reduce.py:24-29, and folds the whole
+    # tensor into the partial result); parity with the reference comes first, so the one-pass
+    # kernel is used exactly where the tree computes the per-row reduction.
+    n = t.shape[axis] if 0 <= axis < len(t.shape) else 0
+    if axis == 0 and n > 0 and n & (n - 1) == 0:
         out = _axis0(t, kind, keepdims)
         if out is not None:
             return out

@@ -24,9 +24,18 @@ def _gather1(rng, out_span):
 def _source(rng, w, h, dtype):
     """One source whose view chain maps it onto an output of w*h elements -> (ends, vals, views)."""
     span = w * h
-    kind = rng.choice(["none", "gather1", "gather2", "scatter", "affine", "chain"])
+    kind = rng.choice(["none", "gather1", "gather2", "scatter", "affine", "chain", "sparse_gather"])
     dens = rng.choice([0.01, 0.1, 0.6])
-    if kind == "gather1":
+    if kind == "sparse_gather":
+        # a wide stride over run-dense data: long groups of raw runs collapse onto one output
+        # coordinate (the tile partition has to cut them)
+        cs = int(rng.integers(20, 60))
+        c0 = int(rng.integers(0, cs))
+        c1 = c0 + (span - 1) * cs + 1
+        n = c1 + int(rng.integers(0, cs))
+        views = [("gather", (n,), [(c0, c1, cs)])]
+        dens = 0.9
+    elif kind == "gather1":
         n, v = _gather1(rng, span)
         views = [v]
     elif kind == "chain":                     # slice of a slice: innermost view first
