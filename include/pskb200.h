@@ -178,7 +178,7 @@ PSK_API psk_status psk_set_jit_threshold(int64_t min_total_runs);
 PSK_API psk_status psk_set_small_partition(int64_t max_samples);
 /* Dense <-> RLE conversion of int32 / float32 buffers (psk_store_from_dense*, psk_store_to_dense*)
  * with 16-byte loads and stores when the dense device pointer is 16-byte aligned.  Results are
- * identical; off by default (the vector kernels are new and have not been timed on a B200 yet). */
+ * identical; on by default (measured on the B200: 1.2-1.7 x the scalar kernels, profiles/r2_summary.md). */
 PSK_API psk_status psk_set_vector_conversion(int32_t enable);
 /* NVRTC stage of the specialisation only (needs no GPU): 0 when the kernel specialised for
  * `prog` over k sources compiles to an sm_100a cubin; the compiler log goes to `log`. */

@@ -274,7 +274,7 @@ class Lib:
     def set_jit_threshold(self, min_total_runs: int):
         self._chk(self.c.psk_set_jit_threshold(C.c_int64(min_total_runs)))
 
-    def set_tile_geometry(self, threads: int, cap: int, regions: int = 4):
+    def set_tile_geometry(self, threads: int, cap: int, regions: int = 2):
         self._chk(self.c.psk_set_tile_geometry(C.c_int32(threads), C.c_int32(cap), C.c_int32(regions)))
 
     def set_vector_conversion(self, enable: bool):

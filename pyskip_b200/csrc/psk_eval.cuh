@@ -58,7 +58,7 @@ constexpr int kTileRegion = kTileCap + kTileSlack;  // pairs per shared-memory r
 // dynamic shared memory of k_merge_eval: regions A | B (| C) of 8-byte pairs
 constexpr int kTileRegions = 2;  // A: the tile's runs; B: the spans the threads keep
 #ifndef PSK_PARK_DEPTH
-#define PSK_PARK_DEPTH 4
+#define PSK_PARK_DEPTH 2
 #endif
 // Finished tiles whose place in the output is not known yet are parked in a per-CTA ring in
 // global memory (it stays in L2) and moved to their place a few tiles later, so a CTA never
@@ -285,17 +285,19 @@ __global__ void __launch_bounds__(kPartBlock) k_partition(DPlan* p) {
     kmax = imax(kmax, s_max[w]);
   }
   // window of every source: samples [#keys < kmin, #keys <= kmax); one warp per source
-  for (int q = warp; q < k; q += kPartBlock / 32) {
-    const int32_t lo = warp_count_samples(p->src[q], s_ns[q], S, kmin, false);
-    const int32_t hi = warp_count_samples(p->src[q], s_ns[q], S, kmax, true);
+  // (the two searches of a source run in different warps, i.e. at the same time)
+  for (int job = warp; job < 2 * k; job += kPartBlock / 32) {
+    const int q = job >> 1;
+    const bool upper = (job & 1) != 0;
+    const int32_t c = warp_count_samples(p->src[q], s_ns[q], S, upper ? kmax : kmin, upper);
     if (lane == 0) {
-      s_wlo[q] = lo;
-      s_wn[q] = hi - lo;
+      if (upper) s_wn[q] = c; else s_wlo[q] = c;
     }
   }
   __syncthreads();
   if (tid == 0) {  // pool layout: windows that do not fit are searched in global memory
     int32_t used = 0;
+    for (int q = 0; q < k; ++q) s_wn[q] -= s_wlo[q];
     for (int q = 0; q < k; ++q) {
       if (used + s_wn[q] <= kPartPool) {
         s_woff[q] = used;

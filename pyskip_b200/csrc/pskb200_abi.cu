@@ -59,7 +59,7 @@ struct Ctx {
   unsigned long long phase_cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int64_t jit_min_runs = 1 << 14;  // evaluations at least this large get a specialised kernel
   int64_t jit_launches = 0;
-  bool convert_vec = false;        // dense <-> RLE with 16-byte accesses (psk_set_vector_conversion)
+  bool convert_vec = true;         // dense <-> RLE with 16-byte accesses (psk_set_vector_conversion)
   int64_t small_partition = 2048;  // samples up to which one block does the whole partition
   int stagger_ns = 0;
   int jit_T = 256, jit_CAP = 4096, jit_regions = kParkDepth;  // tile geometry / park depth of the specialised kernels (PSKB200_TILE_*)
@@ -334,9 +334,12 @@ template <int ELEM>  // payload bytes: 4, 1 (char, sign-extended), -1 (bool)
 __global__ void k_interleave(const int32_t* ends, const void* vals, int32_t n, int2* runs, int32_t* d_count,
                              int32_t* flag) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  // (the arrays may be pinned HOST memory read over PCIe: every element is loaded once, the
+  // predecessor's end comes from the neighbouring lane)
+  const int32_t e = i < n ? ends[i] : 0;
+  int32_t prev = __shfl_up_sync(0xffffffffu, e, 1);
+  if ((threadIdx.x & 31) == 0) prev = (i > 0 && i < n) ? ends[i - 1] : 0;
   if (i < n) {
-    const int32_t e = ends[i];
-    const int32_t prev = i ? ends[i - 1] : 0;
     if (e <= prev) atomicOr(flag, 1);
     uint32_t v;
     if (ELEM == 4) v = reinterpret_cast<const uint32_t*>(vals)[i];
@@ -401,6 +404,25 @@ __global__ void k_fill_one(int2* runs, int32_t* d_count, int32_t span, uint32_t 
     runs[2] = make_int2(kSentinel, 0);
     *d_count = 1;
   }
+}
+
+// Is [p, p + bytes) pinned host memory that kernels can address (cudaHostAlloc / cudaHostRegister)?
+// Then the transfer kernels read / write it in place over PCIe: no staging copy, no staging
+// allocation, and the interleave happens on the way.
+bool device_visible_host(const void* p, void** dev_ptr) {
+#ifdef PSK_CPU_SIM
+  *dev_ptr = const_cast<void*>(p);
+  return true;
+#else
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return false;
+  *dev_ptr = a.devicePointer;
+  return true;
+#endif
 }
 
 // d_ends / d_vals (device, SoA) -> pairs of store s on `stream`; *flag accumulates violations
@@ -708,17 +730,25 @@ psk_status psk_store_from_runs_async(psk_dtype dtype, int64_t nruns, const int32
   s->capacity = nruns;
   s->nruns = nruns;
   s->span = ends[nruns - 1];  // host memory: readable here
-  // everything on the upload stream: staging, copies, interleave + validation
-  unsigned char* tmp = nullptr;
-  const size_t half = ((size_t)nruns * 4 + 15) & ~(size_t)15;
+  // everything on the upload stream.  Pinned host arrays are read in place by the interleave
+  // kernel (zero-copy over PCIe); pageable ones are staged through a device buffer first.
   cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&s->d_runs), (size_t)(nruns + kStorePad) * 8, g.h2d);
-  if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&tmp), 2 * half, g.h2d);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, ends, (size_t)nruns * 4, cudaMemcpyHostToDevice, g.h2d);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(tmp + half, vals, (size_t)nruns * 4, cudaMemcpyHostToDevice, g.h2d);
   if (e == cudaSuccess) {
     s->d_count = reinterpret_cast<int32_t*>(s->d_runs + nruns + kStorePad - 1);
-    launch_interleave(s, reinterpret_cast<int32_t*>(tmp), tmp + half, nruns, g.d_async_err, g.h2d);
-    e = cudaFreeAsync(tmp, g.h2d);
+    void *de = nullptr, *dv = nullptr;
+    if (device_visible_host(ends, &de) && device_visible_host(vals, &dv)) {
+      launch_interleave(s, reinterpret_cast<const int32_t*>(de), dv, nruns, g.d_async_err, g.h2d);
+    } else {
+      unsigned char* tmp = nullptr;
+      const size_t half = ((size_t)nruns * 4 + 15) & ~(size_t)15;
+      e = cudaMallocAsync(reinterpret_cast<void**>(&tmp), 2 * half, g.h2d);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, ends, (size_t)nruns * 4, cudaMemcpyHostToDevice, g.h2d);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(tmp + half, vals, (size_t)nruns * 4, cudaMemcpyHostToDevice, g.h2d);
+      if (e == cudaSuccess) {
+        launch_interleave(s, reinterpret_cast<int32_t*>(tmp), tmp + half, nruns, g.d_async_err, g.h2d);
+        e = cudaFreeAsync(tmp, g.h2d);
+      }
+    }
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventRecord(s->ready, g.h2d);
@@ -743,15 +773,23 @@ psk_status psk_store_runs_async(psk_store_t s, int32_t* ends, void* vals) {
   CUDA_TRY(cudaEventRecord(g.xev, g.stream));
   CUDA_TRY(cudaStreamWaitEvent(g.d2h, g.xev, 0));
   if (s->ready) CUDA_TRY(cudaStreamWaitEvent(g.d2h, s->ready, 0));
-  unsigned char* tmp = nullptr;
-  const size_t half = (n * 4 + 15) & ~(size_t)15;
-  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&tmp), 2 * half, g.d2h));
-  PSK_LAUNCH(k_deinterleave<4>, (unsigned)((n + 255) / 256), 256, 0, g.d2h, s->d_runs, (int32_t)n,
-             reinterpret_cast<int32_t*>(tmp), tmp + half);
-  g.launches.fetch_add(1, std::memory_order_relaxed);
-  CUDA_TRY(cudaMemcpyAsync(ends, tmp, n * 4, cudaMemcpyDeviceToHost, g.d2h));
-  CUDA_TRY(cudaMemcpyAsync(vals, tmp + half, n * 4, cudaMemcpyDeviceToHost, g.d2h));
-  CUDA_TRY(cudaFreeAsync(tmp, g.d2h));
+  void *de = nullptr, *dv = nullptr;
+  if (device_visible_host(ends, &de) && device_visible_host(vals, &dv)) {
+    // pinned destination: the de-interleave kernel writes it in place (zero-copy over PCIe)
+    PSK_LAUNCH(k_deinterleave<4>, (unsigned)((n + 255) / 256), 256, 0, g.d2h, s->d_runs, (int32_t)n,
+               reinterpret_cast<int32_t*>(de), dv);
+    g.launches.fetch_add(1, std::memory_order_relaxed);
+  } else {
+    unsigned char* tmp = nullptr;
+    const size_t half = (n * 4 + 15) & ~(size_t)15;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&tmp), 2 * half, g.d2h));
+    PSK_LAUNCH(k_deinterleave<4>, (unsigned)((n + 255) / 256), 256, 0, g.d2h, s->d_runs, (int32_t)n,
+               reinterpret_cast<int32_t*>(tmp), tmp + half);
+    g.launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaMemcpyAsync(ends, tmp, n * 4, cudaMemcpyDeviceToHost, g.d2h));
+    CUDA_TRY(cudaMemcpyAsync(vals, tmp + half, n * 4, cudaMemcpyDeviceToHost, g.d2h));
+    CUDA_TRY(cudaFreeAsync(tmp, g.d2h));
+  }
   if (!s->busy) CUDA_TRY(cudaEventCreateWithFlags(&s->busy, cudaEventDisableTiming));
   CUDA_TRY(cudaEventRecord(s->busy, g.d2h));
   return PSK_OK;

@@ -16,7 +16,7 @@ import argparse
 ap = argparse.ArgumentParser()
 ap.add_argument("--threads", type=int, default=0)
 ap.add_argument("--cap", type=int, default=0)
-ap.add_argument("--regions", type=int, default=4, help="park depth")
+ap.add_argument("--regions", type=int, default=2, help="park depth")
 ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--build-only", action="store_true")
 ap.add_argument("--no-phase", action="store_true")

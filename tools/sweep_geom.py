@@ -33,7 +33,7 @@ def main():
     expect = None
     for geom in args.geoms.split(","):
         f = [int(x) for x in geom.split("x")]
-        T, CAP, R = f[0], f[1], (f[2] if len(f) > 2 else 4)
+        T, CAP, R = f[0], f[1], (f[2] if len(f) > 2 else 2)
         lib.set_tile_geometry(T, CAP, R)
         r = lib.eval(srcs, prog, A.F32, A.EQ_BITWISE)  # compiles
         n = r.nruns
