@@ -7,6 +7,10 @@
 // facades (IntArray, FloatArray, ...) live in the pybind module.
 #pragma once
 
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+
 #include <array>
 #include <cmath>
 #include <cstdio>
@@ -299,9 +303,48 @@ class Array {
     return (double)(int32_t)bits;
   }
 
+  // float32 the way the reference prints it (fmt 6 "{}": shortest digits that round-trip, fixed
+  // notation with at least one decimal for exponents in [-4, 16), exponent notation otherwise)
+  static std::string format_float(float f) {
+    if (std::isnan(f)) return std::signbit(f) ? "-nan" : "nan";
+    if (std::isinf(f)) return f < 0 ? "-inf" : "inf";
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, f, std::chars_format::scientific);
+    std::string sci(buf, r.ptr);  // [-]d[.ddd]e[+-]XX
+    std::string out;
+    size_t pos = 0;
+    if (sci[0] == '-') {
+      out = "-";
+      pos = 1;
+    }
+    const size_t epos = sci.find('e');
+    std::string digits;
+    for (size_t i = pos; i < epos; ++i)
+      if (sci[i] != '.') digits += sci[i];
+    const int exp10 = std::atoi(sci.c_str() + epos + 1);
+    if (exp10 >= -4 && exp10 < 16) {
+      if (exp10 >= 0) {
+        if ((int)digits.size() <= exp10 + 1) {
+          out += digits + std::string((size_t)(exp10 + 1) - digits.size(), '0') + ".0";
+        } else {
+          out += digits.substr(0, (size_t)exp10 + 1) + "." + digits.substr((size_t)exp10 + 1);
+        }
+      } else {
+        out += "0." + std::string((size_t)(-exp10 - 1), '0') + digits;
+      }
+    } else {
+      out += digits.substr(0, 1);
+      if (digits.size() > 1) out += "." + digits.substr(1);
+      char eb[16];
+      std::snprintf(eb, sizeof eb, "e%c%02d", exp10 < 0 ? '-' : '+', exp10 < 0 ? -exp10 : exp10);
+      out += eb;
+    }
+    return out;
+  }
+
   std::string format_scalar(double v) const {
     std::ostringstream os;
-    if (dtype_ == PSK_F32) os << (float)v;
+    if (dtype_ == PSK_F32) os << format_float((float)v);
     else if (dtype_ == PSK_BOOL) os << (v != 0 ? "true" : "false");
     else if (dtype_ == PSK_CHAR) os << (char)(int)v;
     else os << (long long)v;

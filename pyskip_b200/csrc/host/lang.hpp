@@ -31,7 +31,7 @@ namespace psk_host {
 constexpr int kMaxWidth = 30;    // sources per launch (PSK_MAX_SOURCES = 32)
 constexpr int kDefaultWidth = 8;   // measured optimum on the 27-tap voxel convolution (profiles/r1_summary.md)
 constexpr int kMaxProgram = 160; // nodes per launch  (PSK_MAX_PROGRAM = 192)
-constexpr int kMaxDepth = 36;    // stack depth       (kMaxStack = 40 in the kernels)
+constexpr int kMaxDepth = 124;   // stack depth       (kMaxStack = 128 in the kernels, as lang.hpp:753)
 
 struct Expr;
 using ExprPtr = std::shared_ptr<Expr>;

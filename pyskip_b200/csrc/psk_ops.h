@@ -170,7 +170,7 @@ PSK_HD bool op_known(int op) {
          (op >= PSK_OP_I2F && op <= PSK_OP_F2C);
 }
 
-constexpr int kMaxStack = 40;
+constexpr int kMaxStack = 128;  // lang::execute_plan_fixed's stack (lang.hpp:753)
 
 // The stack machine of lang::execute_plan_fixed (detail/lang.hpp:754-777) with op-codes in
 // place of function pointers.  `val` holds the current value of every source.
