@@ -874,6 +874,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     }
     pk_head = (pk_head + 1) % (kParkDepth > 0 ? kParkDepth : 1);
     --pk_count;
+    __syncthreads();  // every thread has read its part: the slot may be parked into again
     return true;
   };
 
