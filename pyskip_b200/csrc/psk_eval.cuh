@@ -365,6 +365,8 @@ __global__ void __launch_bounds__(kPartBlock) k_partition(DPlan* p) {
         hi_[u] = sample_run(s, pos, S);  // this run is after it
       }
     }
+    // 4-ary search: three independent probes per source and round, so an interval of S runs
+    // takes log4(S) dependent memory round trips instead of log2(S)
     bool more = true;
     while (more) {
       more = false;
@@ -372,9 +374,26 @@ __global__ void __launch_bounds__(kPartBlock) k_partition(DPlan* p) {
       for (int u = 0; u < W; ++u) {
         const int q = q0 + u;
         if (q < k && lo_[u] < hi_[u]) {
-          const int32_t mid = lo_[u] + ((hi_[u] - lo_[u]) >> 1);
-          const int32_t me = mapped_end(p->src[q], mid);
-          if ((q < i) ? (me <= key) : (me < key)) lo_[u] = mid + 1; else hi_[u] = mid;
+          const DSource& sq = p->src[q];
+          const int32_t lo = lo_[u], hi = hi_[u];
+          const int32_t m2 = lo + ((hi - lo) >> 1);
+          const int32_t m1 = lo + ((m2 - lo) >> 1);
+          const int32_t m3 = m2 + 1 < hi ? m2 + 1 + ((hi - m2 - 1) >> 1) : m2;
+          const int32_t e1 = mapped_end(sq, m1), e2 = mapped_end(sq, m2), e3 = mapped_end(sq, m3);
+          const bool b1 = (q < i) ? (e1 <= key) : (e1 < key);
+          const bool b2 = (q < i) ? (e2 <= key) : (e2 < key);
+          const bool b3 = (q < i) ? (e3 <= key) : (e3 < key);
+          if (!b2) {
+            hi_[u] = m2;
+            if (m1 < m2) {
+              if (b1) lo_[u] = m1 + 1; else hi_[u] = m1;
+            }
+          } else {
+            lo_[u] = m2 + 1;
+            if (m3 > m2) {
+              if (b3) lo_[u] = m3 + 1; else hi_[u] = m3;
+            }
+          }
           more = true;
         }
       }
