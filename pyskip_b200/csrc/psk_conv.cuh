@@ -243,228 +243,4 @@ __global__ void __launch_bounds__(kConvRowThreads) k_conv_rows(ConvParams p) {
 }
 
 
-// ---------------------------------------------------------------------------------------
-// k_conv_rows_tree: the same sweep with the stream heads in a per-thread TOURNAMENT TREE in
-// shared memory (what eval::TournamentTree, eval.hpp:43-87, is on the CPU).
-//
-// In k_conv_rows every step tests all KW*KH*KD streams (the lanes of a warp advance different
-// streams, so the test-and-advance code of every stream runs at every step: ~300 instructions
-// per event at 27 taps).  Here a step costs O(log taps): the winner (smallest head) sits in a
-// register; the stream that ended is advanced -- its cursor and value live in shared memory,
-// indexed by the stream number -- and replayed along its leaf-to-root path (5 nodes at 27
-// taps: one load, one compare, one conditional store each).  Integer tap sums are updated
-// incrementally (acc += w * (new - old), exact modulo 2^32); float sums are recomputed in tap
-// order at every distinct end, as the reference's arithmetic demands.  A node is one 32-bit
-// word: (head << 5) | stream, so rows must be shorter than 2^26 (else k_conv_rows runs).
-// Layout [slot][thread]: conflict-free for any combination of slots.
-constexpr int kConvTreeLeaves = 32;
-
-template <int KW, int KH, int KD, bool IS_F>
-struct ConvTree {
-  static constexpr int NR = KH * KD;
-  static constexpr int NS = NR * KW;
-  static constexpr int T = kConvRowThreads;
-  int32_t* tree;    // [kConvTreeLeaves][T] losers of the internal nodes (node 0 unused)
-  int32_t* cur;     // [NS][T] run index of every stream's current piece
-  uint32_t* val;    // [NS][T] value of every stream's current piece
-  int32_t win;      // packed (head << 5) | stream of the overall winner
-  uint32_t acc;     // integer tap sum (maintained incrementally)
-  int32_t y, z;
-
-  PSK_D static int32_t pack(int32_t head, int s) { return head >= (1 << 26) ? kSentinel : (head << 5) | s; }
-
-  PSK_D int32_t rowbase_of(const ConvParams& p, int r) const {
-    const int b = r % KH, c = r / KH;
-    return ((z + c - p.pz) * p.H + (y + b - p.py)) * p.W;
-  }
-
-  PSK_D void init(const ConvParams& p, int32_t y_, int32_t z_) {
-    const int tid = threadIdx.x;
-    y = y_;
-    z = z_;
-    int32_t key[kConvTreeLeaves];
-    acc = 0;
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      const int b = r % KH, c = r / KH;
-      const int32_t iy = y + b - p.py, iz = z + c - p.pz;
-      const bool valid = iy >= 0 && iy < p.H && iz >= 0 && iz < p.D;
-      const int32_t rowid = iz * p.H + iy;
-      const int32_t rb = valid ? rowid * p.W : 0;
-      const int32_t rs = valid ? p.row_start[rowid] : 0;
-#pragma unroll
-      for (int a = 0; a < KW; ++a) {
-        const int s = r * KW + a;
-        const int32_t x0 = a - p.px;  // input x of output x = 0
-        uint32_t v = p.fill;
-        int32_t head = kSentinel, c_ = rs - 1;
-        if (valid && x0 < p.W) {
-          if (x0 < 0) {
-            head = -x0;  // left padding
-          } else {
-            c_ = rs;
-            int2 run = ld_nc(p.runs + c_);
-            while (run.x - rb <= x0) run = ld_nc(p.runs + (++c_));
-            v = (uint32_t)run.y;
-            head = imin(run.x - rb, p.W) - x0;
-          }
-        }
-        cur[s * T + tid] = c_;
-        val[s * T + tid] = v;
-        acc += p.w[s] * v;
-        key[s] = head == kSentinel ? kSentinel : pack(head, s);
-      }
-    }
-#pragma unroll
-    for (int s = NS; s < kConvTreeLeaves; ++s) key[s] = kSentinel;
-    // play the tournament bottom-up: node n keeps the loser, the winner moves up
-#pragma unroll
-    for (int width = kConvTreeLeaves / 2; width >= 1; width >>= 1) {
-#pragma unroll
-      for (int i = 0; i < width; ++i) {
-        const int32_t a_ = key[2 * i], b_ = key[2 * i + 1];
-        tree[(width + i) * T + tid] = imax(a_, b_);
-        key[i] = imin(a_, b_);
-      }
-    }
-    win = key[0];
-  }
-
-  // the winner's stream moves on to its next piece and is replayed up the tree
-  PSK_D void advance(const ConvParams& p, int32_t e) {
-    const int tid = threadIdx.x;
-    const int s = win & 31;
-    const int r = s / KW, a = s - r * KW;
-    const int32_t shift = p.px - a;
-    int32_t head = kSentinel;
-    uint32_t v = p.fill;
-    const uint32_t old = val[s * T + tid];
-    if (e != p.W + shift) {  // else: the row is finished, right padding
-      const int32_t c_ = cur[s * T + tid] + 1;
-      const int2 run = ld_nc(p.runs + c_);
-      cur[s * T + tid] = c_;
-      v = (uint32_t)run.y;
-      head = imin(run.x - rowbase_of(p, r), p.W) + shift;
-    }
-    val[s * T + tid] = v;
-    if (!IS_F) acc += p.w[s] * (v - old);
-    int32_t cand = head == kSentinel ? kSentinel : pack(head, s);
-#pragma unroll
-    for (int node = (kConvTreeLeaves + s) >> 1, l = 0; l < 5; ++l, node >>= 1) {
-      const int32_t loser = tree[node * T + tid];
-      if (loser < cand) {
-        tree[node * T + tid] = cand;
-        cand = loser;
-      }
-    }
-    win = cand;
-  }
-
-  PSK_D uint32_t eval(const ConvParams& p) const {
-    if (!IS_F) return acc;
-    const int tid = threadIdx.x;
-    float f = 0.0f;
-#pragma unroll
-    for (int s = 0; s < NS; ++s) f = f + u2f(p.w[s]) * u2f(val[s * T + tid]);
-    return f2u(f);
-  }
-
-  template <bool WRITE>
-  PSK_D int32_t sweep(const ConvParams& p, int32_t y_, int32_t z_, int2* dst, uint32_t* fv, uint32_t* lv) {
-    init(p, y_, z_);
-    const int32_t rowflat = (z * p.OH + y) * p.OW;
-    const bool typed = p.typed_float != 0;
-    int32_t n = 0, pe = 0;
-    uint32_t pv = 0;
-    bool have = false;
-    for (;;) {
-      int32_t e = win == kSentinel ? p.OW : (win >> 5);
-      if (e > p.OW) e = p.OW;
-      const uint32_t v = eval(p);
-      if (!have) {
-        *fv = v;
-      } else if (!payload_equal(pv, v, typed)) {
-        if (WRITE) dst[n] = make_int2(rowflat + pe, (int32_t)pv);
-        ++n;
-      }
-      pe = e;
-      pv = v;
-      have = true;
-      if (e >= p.OW) break;
-      do {
-        advance(p, e);
-      } while (win != kSentinel && (win >> 5) == e);
-    }
-    *lv = pv;
-    return n;
-  }
-
-  PSK_D uint32_t first_value(const ConvParams& p, int32_t y_, int32_t z_) {
-    init(p, y_, z_);
-    return eval(p);
-  }
-};
-
-template <int KW, int KH, int KD, bool IS_F>
-__global__ void __launch_bounds__(kConvRowThreads) k_conv_rows_tree(ConvParams p) {
-  constexpr int T = kConvRowThreads;
-  constexpr int NS = KW * KH * KD;
-  __shared__ int32_t s_tree[kConvTreeLeaves * T];
-  __shared__ int32_t s_cur[NS * T];
-  __shared__ uint32_t s_val[NS * T];
-  __shared__ uint32_t s_fv[T + 1];
-  __shared__ int32_t s_warp[T / 32 + 2];
-  __shared__ int32_t s_lbsum[LookW<T>::value * (T / 32)];
-  __shared__ int32_t s_lbhas[LookW<T>::value * (T / 32)];
-  __shared__ int32_t s_tile;
-  const int tid = threadIdx.x;
-  if (tid == 0) s_tile = atomicAdd(&p.ctrl[CTRL_TICKET], 1);
-  __syncthreads();
-  const int32_t tile = s_tile;
-  const int32_t nrows = p.OH * p.OD;
-  const int32_t n_tiles = (nrows + T - 1) / T;
-  if (tile >= n_tiles) return;
-  const int32_t row = tile * T + tid;
-  const bool active = row < nrows;
-  const int32_t y = active ? row % p.OH : 0, z = active ? row / p.OH : 0;
-
-  ConvTree<KW, KH, KD, IS_F> ct;
-  ct.tree = s_tree;
-  ct.cur = s_cur;
-  ct.val = s_val;
-  uint32_t fv = 0, lv = 0;
-  int32_t cnt = 0;
-  if (active) cnt = ct.template sweep<false>(p, y, z, nullptr, &fv, &lv);
-  s_fv[tid] = fv;
-  if (tid == T - 1) {  // first value of the row behind the tile
-    const int32_t nrow = tile * T + T;
-    s_fv[T] = nrow < nrows ? ct.first_value(p, nrow % p.OH, nrow / p.OH) : 0u;
-  }
-  __syncthreads();
-  const bool keep_last = active && (row == nrows - 1 || !payload_equal(lv, s_fv[tid + 1], p.typed_float != 0));
-  const int32_t n = cnt + (keep_last ? 1 : 0);
-  int32_t total;
-  const int32_t ofs = block_exclusive_scan<T>(n, s_warp, &total);
-  if (tid == 0) publish_aggregate(p.tile_state, tile, total);
-  const int32_t gofs = lookback_exclusive_cta<T>(p.tile_state, tile, total, s_lbsum, s_lbhas);
-  if (tid == 0 && tile == n_tiles - 1) {
-    const int32_t c = gofs + total;
-    p.ctrl[CTRL_COUNT] = c;
-    *p.out_count = c;
-    if (c <= p.out_capacity) {
-      p.out[c] = make_int2(kSentinel, 0);
-      p.out[c + 1] = make_int2(kSentinel, 0);
-    }
-  }
-  if (gofs + total > p.out_capacity) {
-    if (tid == 0) p.ctrl[CTRL_ERROR] = 2;
-    return;
-  }
-  if (active) {
-    int2* const dst = p.out + gofs + ofs;
-    ct.template sweep<true>(p, y, z, dst, &fv, &lv);
-    if (keep_last) dst[cnt] = make_int2((z * p.OH + y) * p.OW + p.OW, (int32_t)lv);
-  }
-}
-
 }  // namespace psk

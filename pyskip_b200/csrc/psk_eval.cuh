@@ -473,7 +473,7 @@ PSK_D int32_t block_exclusive_scan(int32_t v, int32_t* s_warp /*[T/32+1]*/, int3
   __syncthreads();
   int32_t excl = s_warp[warp] + inc - v;
   *total = s_warp[T / 32];
-  __syncthreads();
+  // (no trailing barrier: every caller passes another barrier before s_warp is written again)
   return excl;
 }
 
@@ -585,7 +585,7 @@ PSK_D bool lookback_try(unsigned long long* state, int32_t tile, int32_t count, 
   int32_t excl = 0;
   bool ok = true;
   if (tile > 0) {
-    __syncthreads();  // s_sum / s_has free
+    // (s_sum / s_has: the caller has passed a barrier since their last readers)
 #pragma unroll
     for (int u = 0; u < kLookW; ++u) {
       const int32_t idx = tile - (1 + tid + T * u);
@@ -824,6 +824,10 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
 #pragma unroll
   for (int u = 0; u < kLookWMax; ++u) look.w[u] = 0ull;
   int2* const park = views ? nullptr : p->park + (long long)blockIdx.x * kParkDepth * kTileCap;
+  // plan fields of the tile loop, read once (the plan lives in global memory)
+  unsigned long long* const tile_state = p->tile_state;
+  int2* const out = p->out;
+  const int32_t out_capacity = p->out_capacity;
 
   PSK_PHASE_DECL;
   // the last tile also leaves the run count and the sentinel pairs behind
@@ -831,9 +835,9 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     if (tid == 0 && ftile == n_tiles - 1) {
       p->ctrl[CTRL_COUNT] = cnt;
       *p->out_count = cnt;  // the count stays on the device too (queued consumers)
-      if (cnt <= p->out_capacity) {
-        p->out[cnt] = make_int2(kSentinel, 0);
-        p->out[cnt + 1] = make_int2(kSentinel, 0);
+      if (cnt <= out_capacity) {
+        out[cnt] = make_int2(kSentinel, 0);
+        out[cnt + 1] = make_int2(kSentinel, 0);
       }
     }
   };
@@ -853,9 +857,9 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
   };
   // with views: global offset by a blocking look-back, spans straight to their place
   auto flush_direct = [&](int32_t ftile, int32_t ftotal, int32_t fn, int32_t fbase, int32_t fofs, int fregion) {
-    const int32_t gofs = lookback_exclusive_cta<T>(p->tile_state, ftile, ftotal, s_lbsum, s_lbhas);
+    const int32_t gofs = lookback_exclusive_cta<T>(tile_state, ftile, ftotal, s_lbsum, s_lbhas);
     finish_output(ftile, gofs + ftotal);
-    if (gofs + ftotal <= p->out_capacity) store_spans(p->out, gofs + fofs, fregion + fbase, fn);
+    if (gofs + ftotal <= out_capacity) store_spans(out, gofs + fofs, fregion + fbase, fn);
     else if (tid == 0) p->ctrl[CTRL_ERROR] = 2;
     __syncthreads();  // the span region may be overwritten now
   };
@@ -864,19 +868,21 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
   auto unpark = [&](bool block) -> bool {
     const int32_t ftile = s_pk_tile[pk_head], ftotal = s_pk_total[pk_head];
     int32_t gofs = 0;
-    bool ok = look_tile == ftile && lookback_try<T>(p->tile_state, ftile, ftotal, look, &gofs, s_lbsum, s_lbhas);
+    if (block) __syncthreads();  // (the fold arrays may still be read from a previous attempt)
+    bool ok = look_tile == ftile && lookback_try<T>(tile_state, ftile, ftotal, look, &gofs, s_lbsum, s_lbhas);
     while (!ok && block) {
-      look = lookback_issue<T>(p->tile_state, ftile, 0);
+      look = lookback_issue<T>(tile_state, ftile, 0);
       look_tile = ftile;
-      ok = lookback_try<T>(p->tile_state, ftile, ftotal, look, &gofs, s_lbsum, s_lbhas);
+      __syncthreads();
+      ok = lookback_try<T>(tile_state, ftile, ftotal, look, &gofs, s_lbsum, s_lbhas);
       if (!ok) sleep_ns(200);
     }
     look_tile = -1;
     if (!ok) return false;
     finish_output(ftile, gofs + ftotal);
-    if (gofs + ftotal <= p->out_capacity) {
+    if (gofs + ftotal <= out_capacity) {
       const int2* const src = park + (long long)pk_head * kTileCap;
-      int2* const dst = p->out + gofs;
+      int2* const dst = out + gofs;
       // eight loads in flight per thread (every iteration of a plain copy loop would pay the
       // L2 round trip again)
       for (int32_t j0 = tid; j0 < ftotal; j0 += 8 * T) {
@@ -893,7 +899,9 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     }
     pk_head = (pk_head + 1) % (kParkDepth > 0 ? kParkDepth : 1);
     --pk_count;
-    __syncthreads();  // every thread has read its part: the slot may be parked into again
+    // every thread must have read its part before the slot is parked into again: the caller of a
+    // blocking call writes at once, everybody else passes the next tile's search barrier first
+    if (block) __syncthreads();
     return true;
   };
 
@@ -913,7 +921,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     mbar_wait(&s_bar, (uint32_t)(it & 1));
     if (pk_count > 0) {
       look_tile = s_pk_tile[pk_head];
-      look = lookback_issue<T>(p->tile_state, look_tile, 0);
+      look = lookback_issue<T>(tile_state, look_tile, 0);
     }
     PSK_PHASE(0);
 
@@ -1124,7 +1132,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     int32_t tile_total;
     const int32_t my_ofs = block_exclusive_scan<T>(n, s_warp, &tile_total);
     PSK_PHASE(4);
-    if (tid == 0) publish_aggregate(p->tile_state, tile, tile_total);
+    if (tid == 0) publish_aggregate(tile_state, tile, tile_total);
     const bool next_valid = s_desc[(it + 1) & 1].tile < n_tiles;
     if (!views) {
       // park the tile's spans (dense, in tile order) in this CTA's ring; a full ring first

@@ -222,12 +222,24 @@ PSK_D void sleep_ns(unsigned ns) {
 #endif
 }
 
-// volatile / relaxed accessors used by the decoupled look-back chain
+// relaxed device-scope accessors used by the decoupled look-back chain (a word carries both
+// status and count, so no ordering with other memory is needed; device scope is enough --
+// `volatile` would compile to system-scope accesses)
 PSK_D unsigned long long ld_volatile_u64(const unsigned long long* p) {
+#if defined(__CUDA_ARCH__)
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+#else
   return *reinterpret_cast<const volatile unsigned long long*>(p);
+#endif
 }
 PSK_D void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#else
   *reinterpret_cast<volatile unsigned long long*>(p) = v;
+#endif
 }
 
 }  // namespace psk

@@ -64,7 +64,6 @@ struct Ctx {
   int stagger_ns = 0;
   int jit_T = 256, jit_CAP = 4096, jit_regions = kParkDepth;  // tile geometry / park depth of the specialised kernels (PSKB200_TILE_*)
   cudaEvent_t xev = nullptr;                     // orders the download stream behind the library stream
-  bool conv_tree = true;                         // stencil kernel variant (PSKB200_CONV_TREE=0: all streams in registers)
   unsigned long long* trace_buf = nullptr;  // PSK_PHASE_TIMING builds: device trace buffer
   int64_t trace_cap = 0, trace_tiles = 0;
   // psk_eval_async: a ring of in-flight evaluations, each with its own pinned plan staging,
@@ -170,7 +169,6 @@ psk_status do_init(int device) {
     const int t = atoi(sv);
     if (t >= 32 && t <= 1024 && t % 32 == 0) g.jit_T = t;
   }
-  if (const char* sv = getenv("PSKB200_CONV_TREE")) g.conv_tree = atoi(sv) != 0;
   if (const char* sv = getenv("PSKB200_PARK_DEPTH")) {
     const int r = atoi(sv);
     if (r >= 1 && r <= 16) g.jit_regions = r;
@@ -470,14 +468,7 @@ psk_status encode_device(const void* d_dense, int64_t n, psk_store_t* out) {
 
 namespace {
 template <int KW, int KH, int KD>
-void launch_conv(bool is_f, bool tree, unsigned grid, const ConvParams& cp) {
-  if (tree) {  // stream heads in a per-thread tournament tree (rows shorter than 2^26)
-    auto kf = k_conv_rows_tree<KW, KH, KD, true>;
-    auto ki = k_conv_rows_tree<KW, KH, KD, false>;
-    if (is_f) LAUNCH(kf, grid, kConvRowThreads, 0, cp);
-    else LAUNCH(ki, grid, kConvRowThreads, 0, cp);
-    return;
-  }
+void launch_conv(bool is_f, unsigned grid, const ConvParams& cp) {
   auto kf = k_conv_rows<KW, KH, KD, true>;
   auto ki = k_conv_rows<KW, KH, KD, false>;
   if (is_f) LAUNCH(kf, grid, kConvRowThreads, 0, cp);
@@ -1429,9 +1420,8 @@ psk_status psk_conv_nd(psk_store_t s, int32_t ndim, const int32_t* shape, const 
     LAUNCH(k_conv_row_starts, (unsigned)((in_rows + 255) / 256), 256, 0, cp);
     const bool is_f = s->dtype == PSK_F32;
     if (g.profile) cudaEventRecord(g.pev0, g.stream);
-    const bool tree = g.conv_tree && (int64_t)cp.OW + 1 < (1LL << 26) && (int64_t)cp.W + cp.px + 1 < (1LL << 26);
-    if (ndim == 3) launch_conv<3, 3, 3>(is_f, tree, (unsigned)n_tiles, cp);
-    else launch_conv<3, 3, 1>(is_f, tree, (unsigned)n_tiles, cp);
+    if (ndim == 3) launch_conv<3, 3, 3>(is_f, (unsigned)n_tiles, cp);
+    else launch_conv<3, 3, 1>(is_f, (unsigned)n_tiles, cp);
     if (g.profile) cudaEventRecord(g.pev1, g.stream);
     e = cudaGetLastError();
   }
