@@ -73,7 +73,24 @@ constexpr int kCtasPerSm = kCtasBySmem < kCtasByThreads ? (kCtasBySmem < 1 ? 1 :
 // Development aid (-DPSK_PHASE_TIMING, tools/phase_profile.py): thread 0 of every CTA adds the
 // clock64() cycles it spends in each phase of the tile loop to p->phase[].  Not compiled into
 // the product library.
-#ifdef PSK_PHASE_TIMING
+#ifdef PSK_PARTITION_TIMING  // the same for k_partition (tools/phase_profile.py --partition)
+#define PSK_PHASE_TIMING
+#define PSK_PPHASE_DECL long long pp_t = clock64()
+#define PSK_PPHASE(i)                                                     \
+  do {                                                                    \
+    if (threadIdx.x == 0) {                                               \
+      long long now_ = clock64();                                         \
+      atomicAdd(&p->phase[i], (unsigned long long)(now_ - pp_t));         \
+      pp_t = now_;                                                        \
+    }                                                                     \
+  } while (0)
+#define PSK_PPHASE_ANY(i, since) atomicAdd(&p->phase[i], (unsigned long long)(clock64() - (since)))
+#else
+#define PSK_PPHASE_DECL
+#define PSK_PPHASE(i)
+#define PSK_PPHASE_ANY(i, since)
+#endif
+#if defined(PSK_PHASE_TIMING) && !defined(PSK_PARTITION_TIMING)
 #define PSK_PHASE_DECL long long ph_t = clock64(); long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define PSK_PHASE(i)                                                              \
   do {                                                                            \
@@ -128,14 +145,31 @@ PSK_D int32_t warp_bound_mapped(const DSource& s, int32_t lo, int32_t hi, int32_
   return lo + __popc(__ballot_sync(0xffffffffu, before));
 }
 
-// sample j of a source = its run a + min((j + 1) S, n) - 1 (the last sample is the last run)
-PSK_D int32_t sample_run(const DSource& s, int32_t j, int32_t S) {
-  int32_t n = s.e - s.a;
-  int32_t off = (j + 1) * S;
-  if (off > n) off = n;
-  return s.a + off - 1;
+// Samples of a source: the runs of [a, e) whose index g has (g + 1) % S == 0 -- aligned to the
+// run array, not to a, so that they can be read from the store's compact index -- and the last
+// run e - 1.  Between two samples lie fewer than S runs.
+PSK_HD int32_t first_sample(int32_t a, int32_t S) { return (a / S + 1) * S - 1; }
+PSK_HD int32_t sample_count(int32_t a, int32_t e, int32_t S) {
+  if (e <= a) return 0;
+  const int32_t g0 = first_sample(a, S);
+  return (e - 2 >= g0 ? (e - 2 - g0) / S + 1 : 0) + 1;
 }
-PSK_D int32_t sample_key(const DSource& s, int32_t j, int32_t S) { return mapped_end(s, sample_run(s, j, S)); }
+PSK_D int32_t sample_run(const DSource& s, int32_t j, int32_t S) {
+  return j + 1 < s.ns ? s.g0 + j * S : s.e - 1;
+}
+// the mapped end of run g, read from the compact index where g is on its grid
+PSK_D int32_t indexed_end(const DSource& s, int32_t g) {
+  int32_t raw;
+  if (s.index != nullptr && ((g + 1) & (kIndexStride - 1)) == 0) raw = ld_nc(s.index + ((g + 1) / kIndexStride - 1));
+  else raw = ld_nc(s.runs + g).x;
+  return s.nviews ? map_chain(s.v, s.nviews, raw) : raw;
+}
+PSK_D int32_t sample_key(const DSource& s, int32_t j, int32_t S) { return indexed_end(s, sample_run(s, j, S)); }
+// runs [lo, hi) between sample pos - 1 and sample pos; run hi is the sample itself
+PSK_D void sample_interval(const DSource& s, int32_t pos, int32_t S, int32_t* lo, int32_t* hi) {
+  *lo = pos == 0 ? s.a : sample_run(s, pos - 1, S) + 1;
+  *hi = sample_run(s, pos, S);
+}
 
 // number of samples of s whose key is <= key (le) or < key (!le); warp-cooperative
 PSK_D int32_t warp_count_samples(const DSource& s, int32_t ns, int32_t S, int32_t key, bool le) {
@@ -161,6 +195,8 @@ PSK_D int32_t warp_count_samples(const DSource& s, int32_t ns, int32_t S, int32_
 }
 
 #ifndef __CUDACC_RTC__  // (the run-time specialisation compiles the merge kernel only)
+constexpr int kPartBlock = 256;  // threads = samples per block of k_partition
+
 // ---------------------------------------------------------------------------------------
 // k_prepare: one warp per source.  [a, e) = runs whose mapped end is in (0, span], cut
 // after the first run that reaches span (everything later is a zero-length mapped run).
@@ -185,15 +221,17 @@ __global__ void k_prepare(DPlan* p) {
       s.nruns = n;
       s.a = a;
       s.e = e;
-      s.ns = (e - a + p->S - 1) / p->S;
+      s.g0 = first_sample(a, p->S);
+      s.ns = sample_count(a, e, p->S);
       s_ns[i] = s.ns;
     }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    int32_t off = 0;
+    int32_t off = 0, blk = 0;
     for (int q = 0; q < k; ++q) {
-      p->src[q].samp_off = off;
+      p->src[q].blk_off = blk;
+      blk += (s_ns[q] + kPartBlock - 1) / kPartBlock;
       off += s_ns[q];
     }
     p->total_samples = off;
@@ -202,17 +240,41 @@ __global__ void k_prepare(DPlan* p) {
   }
 }
 
-// which source owns sample sid: last i with samp_off[i] <= sid (sources without samples
-// share their successor's offset and are skipped)
-PSK_D int sample_owner(const int32_t* s_off, int k, int32_t sid) {
+// which source a block of k_partition works on: last i with blk_off[i] <= b (sources without
+// samples share their successor's offset and are skipped)
+PSK_D int block_owner(const int32_t* s_off, int k, int32_t b) {
   int l = 0, h = k - 1;
   while (l < h) {
     const int mid = (l + h + 1) >> 1;
-    if (s_off[mid] <= sid) l = mid; else h = mid - 1;
+    if (s_off[mid] <= b) l = mid; else h = mid - 1;
   }
   return l;
 }
 
+// samples of source q inside the block's window [wlo, wlo + wn) that come before `key`
+// (<= key if le, else < key); the window's keys are staged at pool[wo ...] unless wo < 0
+PSK_D int32_t window_count(const DSource& s, const int32_t* pool, int32_t wo, int32_t wlo, int32_t wn, int32_t S,
+                           int32_t key, bool le) {
+  if (wo >= 0) {
+    // staged window: branch-free descent over powers of two (the trip count depends on the
+    // window only, so the lanes of a warp stay together); v <= key is v < key + 1
+    const int32_t* w = pool + wo - 1;
+    const int32_t bound = key + (le ? 1 : 0);
+    int32_t pos = 0;
+    for (int32_t step = wn > 0 ? 1 << (31 - __clz(wn)) : 0; step > 0; step >>= 1) {
+      const int32_t np = pos + step;
+      if (np <= wn && w[np] < bound) pos = np;
+    }
+    return pos;
+  }
+  int32_t lo = 0, hi = wn;
+  while (lo < hi) {
+    const int32_t mid = lo + ((hi - lo) >> 1);
+    const int32_t v = sample_key(s, wlo + mid, S);
+    if (le ? (v <= key) : (v < key)) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
 
 // ---------------------------------------------------------------------------------------
 // k_partition: samples -> merged ranks -> tile bounds, in one kernel.
@@ -223,10 +285,12 @@ PSK_D int sample_owner(const int32_t* s_off, int k, int32_t sid) {
 // end < x, and for q = i those up to the sample's own run.  bounds[(t + 1) k + q] is the first
 // run after it.  With views, lookahead[t k + q] is the first run of q whose mapped end is
 // beyond x (it may lie far behind the bound inside a collapsed group of runs), mapped, as a pair.
-constexpr int kPartBlock = 256;
-constexpr int kPartPool = 6144;  // sample keys of the other sources staged per block
+constexpr int kPartPool = 4096;  // sample keys of the other sources staged per block
 
-__global__ void __launch_bounds__(kPartBlock) k_partition(DPlan* p) {
+#ifndef PSK_PART_MINBLOCKS
+#define PSK_PART_MINBLOCKS 5
+#endif
+__global__ void __launch_bounds__(kPartBlock, PSK_PART_MINBLOCKS) k_partition(DPlan* p) {
   __shared__ int32_t s_off[PSK_MAX_SOURCES + 1];
   __shared__ int32_t s_ns[PSK_MAX_SOURCES];
   __shared__ int32_t s_wlo[PSK_MAX_SOURCES];   // window of source q: first sample
@@ -234,9 +298,15 @@ __global__ void __launch_bounds__(kPartBlock) k_partition(DPlan* p) {
   __shared__ int32_t s_woff[PSK_MAX_SOURCES + 1];  // ... offset in s_pool, or -1 (searched in global memory)
   __shared__ int32_t s_pool[kPartPool];
   __shared__ int32_t s_min[kPartBlock / 32], s_max[kPartBlock / 32];
+  __shared__ int32_t s_ckey[kPartBlock], s_cj[kPartBlock], s_ci[kPartBlock], s_ct[kPartBlock];  // the block's closing samples
+  __shared__ int32_t s_nclose;
+#ifdef PSK_PARTITION_TIMING
+  unsigned long long gt0_;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0_));
+#endif
   const int k = p->k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int32_t S = p->S, m = p->m;
-  const int32_t total = p->total_samples, n_tiles = p->n_tiles;
+  const int32_t n_tiles = p->n_tiles;
   const bool any_views = p->any_views != 0;
 
   // housekeeping that would otherwise be memsets: look-back words, control words, the
@@ -255,17 +325,19 @@ __global__ void __launch_bounds__(kPartBlock) k_partition(DPlan* p) {
     }
     if (tid == 0) p->tile_hi[n_tiles - 1] = p->span;
   }
-  if ((long long)blockIdx.x * kPartBlock >= total) return;
-
+  PSK_PPHASE_DECL;
   if (tid < k) {
-    s_off[tid] = p->src[tid].samp_off;
+    s_off[tid] = p->src[tid].blk_off;
     s_ns[tid] = p->src[tid].ns;
   }
+  if (tid == 0) s_nclose = 0;
   __syncthreads();
-  const int32_t sid = blockIdx.x * kPartBlock + tid;
-  const bool valid = sid < total;
-  const int i = valid ? sample_owner(s_off, k, sid) : 0;
-  const int32_t j = valid ? sid - s_off[i] : 0;
+  // a block ranks up to kPartBlock consecutive samples of ONE source, so the key range it has to
+  // stage from the other sources stays narrow
+  const int i = block_owner(s_off, k, (int32_t)blockIdx.x);
+  const int32_t j = ((int32_t)blockIdx.x - s_off[i]) * kPartBlock + tid;
+  const bool valid = j < s_ns[i];
+  if (j - tid >= s_ns[i]) return;  // (the grid is sized for the worst case: whole blocks beyond the samples)
   const int32_t key = valid ? sample_key(p->src[i], j, S) : 0;
   // smallest / largest key of the block
   int32_t kmin = valid ? key : kSentinel, kmax = valid ? key : -1;
@@ -284,6 +356,7 @@ __global__ void __launch_bounds__(kPartBlock) k_partition(DPlan* p) {
     kmin = imin(kmin, s_min[w]);
     kmax = imax(kmax, s_max[w]);
   }
+  PSK_PPHASE(0);
   // window of every source: samples [#keys < kmin, #keys <= kmax); one warp per source
   // (the two searches of a source run in different warps, i.e. at the same time)
   for (int job = warp; job < 2 * k; job += kPartBlock / 32) {
@@ -295,6 +368,7 @@ __global__ void __launch_bounds__(kPartBlock) k_partition(DPlan* p) {
     }
   }
   __syncthreads();
+  PSK_PPHASE(1);
   if (tid == 0) {  // pool layout: windows that do not fit are searched in global memory
     int32_t used = 0;
     for (int q = 0; q < k; ++q) s_wn[q] -= s_wlo[q];
@@ -316,119 +390,100 @@ __global__ void __launch_bounds__(kPartBlock) k_partition(DPlan* p) {
     for (int32_t t = tid; t < wn; t += kPartBlock) s_pool[wo + t] = sample_key(p->src[q], wlo + t, S);
   }
   __syncthreads();
-  if (!valid) return;
+  PSK_PPHASE(2);
   // rank among all samples: own index + samples of every other source that come before
   int32_t rank = j;
-  for (int q = 0; q < k; ++q) {
-    if (q == i) continue;
-    const int32_t wo = s_woff[q];
-    int32_t lo = 0, hi = s_wn[q];
-    const int32_t wlo = s_wlo[q];
-    while (lo < hi) {
-      const int32_t mid = lo + ((hi - lo) >> 1);
-      const int32_t v = wo >= 0 ? s_pool[wo + mid] : sample_key(p->src[q], wlo + mid, S);
-      if ((q < i) ? (v <= key) : (v < key)) lo = mid + 1; else hi = mid;
+  if (valid) {
+    for (int q = 0; q < k; ++q) {
+      if (q == i) continue;
+      rank += s_wlo[q] + window_count(p->src[q], s_pool, s_woff[q], s_wlo[q], s_wn[q], S, key, q < i);
     }
-    rank += wlo + lo;
   }
-  if ((rank + 1) % m != 0) return;
-  const int32_t t = (rank + 1) / m - 1;  // the tile this sample closes
-  if (t + 1 >= n_tiles) return;          // the last tile ends at span
-  p->tile_hi[t] = key;
-  // per source: the first run after the splitter.  Four sources advance in lock step.
-  constexpr int W = 4;
-  for (int q0 = 0; q0 < k; q0 += W) {
-    int32_t lo_[W], hi_[W];
-#pragma unroll
-    for (int u = 0; u < W; ++u) {
-      const int q = q0 + u;
-      lo_[u] = hi_[u] = 0;
-      if (q >= k) continue;
-      const DSource& s = p->src[q];
-      if (q == i) {
-        lo_[u] = hi_[u] = sample_run(s, j, S) + 1;
-        continue;
-      }
-      const int32_t wo = s_woff[q];
-      int32_t lo = 0, hi = s_wn[q];
-      const int32_t wlo = s_wlo[q];
-      while (lo < hi) {
-        const int32_t mid = lo + ((hi - lo) >> 1);
-        const int32_t v = wo >= 0 ? s_pool[wo + mid] : sample_key(s, wlo + mid, S);
-        if ((q < i) ? (v <= key) : (v < key)) lo = mid + 1; else hi = mid;
-      }
-      const int32_t pos = wlo + lo;  // samples of q before the splitter
-      if (pos >= s_ns[q]) {
-        lo_[u] = hi_[u] = s.e;
+  PSK_PPHASE(3);
+  // the samples that close a tile (merged rank = -1 mod m) are collected; the last tile ends at span
+  if (valid && (rank + 1) % m == 0 && (rank + 1) / m < n_tiles) {
+    const int c = atomicAdd(&s_nclose, 1);
+    s_ckey[c] = key;
+    s_cj[c] = j;
+    s_ci[c] = i;
+    s_ct[c] = (rank + 1) / m - 1;
+  }
+  __syncthreads();
+  // Per closing sample and source: the first run after the splitter.  One work item per
+  // (closing sample, source), handled by a group of 8 lanes: the sample interval around the
+  // splitter (< S runs) is narrowed to fewer than kIndexStride runs by the index entries inside
+  // it -- one load per lane -- and those runs are tested in a second round of loads.
+  const int nitems = s_nclose * k;
+  const int grp = tid >> 3, l8 = tid & 7;
+  for (int w0 = 0; w0 < nitems; w0 += kPartBlock / 8) {
+    const int w = w0 + grp;
+    const bool live = w < nitems;
+    const int c = live ? w / k : 0, q = live ? w - c * k : 0;
+    const int32_t ckey = s_ckey[c], ct = s_ct[c];
+    const int ci = s_ci[c];
+    const int32_t cj = s_cj[c];
+    const DSource& s = p->src[q];
+    const bool le = q < ci;  // runs of a source in front of the sample's own tie with it
+    int32_t lo = 0, hi = 0;
+    if (live) {
+      if (q == ci) {
+        lo = hi = sample_run(s, cj, S) + 1;
       } else {
-        lo_[u] = s.a + pos * S;          // runs below are before the splitter
-        hi_[u] = sample_run(s, pos, S);  // this run is after it
+        const int32_t pos = s_wlo[q] + window_count(s, s_pool, s_woff[q], s_wlo[q], s_wn[q], S, ckey, le);
+        if (pos >= s_ns[q]) lo = hi = s.e;
+        else sample_interval(s, pos, S, &lo, &hi);  // runs below lo are before the splitter, run hi is after it
       }
     }
-    // 4-ary search: three independent probes per source and round, so an interval of S runs
-    // takes log4(S) dependent memory round trips instead of log2(S)
-    bool more = true;
-    while (more) {
-      more = false;
-#pragma unroll
-      for (int u = 0; u < W; ++u) {
-        const int q = q0 + u;
-        if (q < k && lo_[u] < hi_[u]) {
-          const DSource& sq = p->src[q];
-          const int32_t lo = lo_[u], hi = hi_[u];
-          const int32_t m2 = lo + ((hi - lo) >> 1);
-          const int32_t m1 = lo + ((m2 - lo) >> 1);
-          const int32_t m3 = m2 + 1 < hi ? m2 + 1 + ((hi - m2 - 1) >> 1) : m2;
-          const int32_t e1 = mapped_end(sq, m1), e2 = mapped_end(sq, m2), e3 = mapped_end(sq, m3);
-          const bool b1 = (q < i) ? (e1 <= key) : (e1 < key);
-          const bool b2 = (q < i) ? (e2 <= key) : (e2 < key);
-          const bool b3 = (q < i) ? (e3 <= key) : (e3 < key);
-          if (!b2) {
-            hi_[u] = m2;
-            if (m1 < m2) {
-              if (b1) lo_[u] = m1 + 1; else hi_[u] = m1;
-            }
-          } else {
-            lo_[u] = m2 + 1;
-            if (m3 > m2) {
-              if (b3) lo_[u] = m3 + 1; else hi_[u] = m3;
-            }
-          }
-          more = true;
-        }
+    {  // (every lane takes part in the shuffles; groups without work pass with lo == hi)
+      const int32_t i0 = lo / kIndexStride, n1 = s.index != nullptr ? hi / kIndexStride - i0 : 0;
+      int32_t cnt = 0;
+      for (int32_t r = l8; r < n1; r += 8) {
+        const int32_t raw = ld_nc(s.index + i0 + r);
+        const int32_t me = s.nviews ? map_chain(s.v, s.nviews, raw) : raw;
+        cnt += (le ? (me <= ckey) : (me < ckey)) ? 1 : 0;
       }
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
+      if (cnt < n1) hi = (i0 + cnt) * kIndexStride + kIndexStride - 1;
+      if (cnt > 0) lo = (i0 + cnt) * kIndexStride;
     }
-#pragma unroll
-    for (int u = 0; u < W; ++u) {
-      const int q = q0 + u;
-      if (q >= k) continue;
-      p->bounds[(t + 1) * k + q] = lo_[u];
+    {
+      int32_t cnt = 0;
+      for (int32_t r = lo + l8; r < hi; r += 8) {
+        const int32_t me = mapped_end(s, r);
+        cnt += (le ? (me <= ckey) : (me < ckey)) ? 1 : 0;
+      }
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
+      lo += cnt;
+    }
+    if (live && l8 == 0) {
+      if (q == ci) p->tile_hi[ct] = ckey;
+      p->bounds[(ct + 1) * k + q] = lo;
       if (any_views) {
         // Look-ahead runs of q behind the tile (mapped, as pairs).  Every run from the bound on
         // has a mapped end >= x.  First: the run that covers the coordinates right behind q's
         // last in-tile run -- the run at the bound unless it maps onto no coordinate (mapped end
         // not beyond its predecessor's: a collapsed group that continues), then the first run
         // beyond x.  Second: the first run beyond x when the first one ends AT x.
-        const DSource& s = p->src[q];
-        const int32_t b = lo_[u];
+        const int32_t b = lo;
         int2 l1 = make_int2(kSentinel, 0), l2 = make_int2(kSentinel, 0);
         if (b < s.e) {
           const int32_t prev = b > s.a ? mapped_end(s, b - 1) : 0;
           int2 r = ld_nc(s.runs + b);
           if (s.nviews) r.x = map_chain(s.v, s.nviews, r.x);
-          int32_t beyond = -1;  // index of the first run whose mapped end is > x, once needed
-          if (r.x > prev) {
-            l1 = r;
-          }
-          if (r.x <= key) {
+          if (r.x > prev) l1 = r;
+          if (r.x <= ckey) {
             // gallop over the runs that end at x
             int32_t step = 1, last = b;
-            while (last + step < s.e && mapped_end(s, last + step) <= key) {
+            while (last + step < s.e && mapped_end(s, last + step) <= ckey) {
               last += step;
               step <<= 1;
             }
             const int32_t top = last + step < s.e ? last + step : s.e;
-            beyond = ub_mapped(s, last + 1, top, key);
+            const int32_t beyond = ub_mapped(s, last + 1, top, ckey);  // first run whose mapped end is > x
             int2 r2 = make_int2(kSentinel, 0);
             if (beyond < s.e) {
               r2 = ld_nc(s.runs + beyond);
@@ -437,11 +492,22 @@ __global__ void __launch_bounds__(kPartBlock) k_partition(DPlan* p) {
             if (r.x > prev) l2 = r2; else l1 = r2;
           }
         }
-        p->lookahead[(t * k + q) * 2] = l1;
-        p->lookahead[(t * k + q) * 2 + 1] = l2;
+        p->lookahead[(ct * k + q) * 2] = l1;
+        p->lookahead[(ct * k + q) * 2 + 1] = l2;
       }
     }
   }
+#ifdef PSK_PARTITION_TIMING
+  PSK_PPHASE(4);
+  if (tid == 0) {
+    unsigned long long gt1_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1_));
+    const unsigned long long mask40 = (1ull << 40) - 1;
+    atomicAdd(&p->phase[5], gt1_ - gt0_);                          // block durations, ns
+    atomicMax(&p->phase[6], gt1_ & mask40);                        // end of the last block ...
+    atomicMax(&p->phase[7], (1ull << 40) - (gt0_ & mask40));       // ... and start of the first one
+  }
+#endif
 }
 
 #endif  // !__CUDACC_RTC__
@@ -761,6 +827,25 @@ PSK_D void issue_tile_copies(const DPlan* p, const TileDesc& d, int k, const Sme
     bulk_g2s(sm.dst(region + inc - seg), p->src[lane].runs + (d.b0[lane] - odd), (uint32_t)seg * 8u, bar);
 }
 
+// One step of the cursor search: first index in [c, c + r) whose end is > key, where the last
+// candidate is known to qualify.  4-ary while the range allows it: three INDEPENDENT probes per
+// step, so a range of n takes log4(n) dependent shared-memory round trips instead of log2(n).
+// The range shrinks by the same amount whatever the outcome (branch-free).
+PSK_D void search_step4(const SmemPairs& sm, int32_t& c, int32_t& r, int32_t key) {
+  if (r >= 4) {
+    const int32_t q = r >> 2;
+    const bool b1 = sm.ldx(c + q - 1) <= key;
+    const bool b2 = sm.ldx(c + 2 * q - 1) <= key;
+    const bool b3 = sm.ldx(c + 3 * q - 1) <= key;
+    c += b3 ? 3 * q : b2 ? 2 * q : b1 ? q : 0;
+    r -= 3 * q;
+  } else {
+    const int32_t half = r >> 1;
+    c += (sm.ldx(c + half - 1) <= key) ? half : 0;
+    r -= half;
+  }
+}
+
 // which source owns flat in-tile slot f: last q with flat[q] <= f
 PSK_D int flat_owner(const int32_t* flat, int k, int32_t f) {
   int l = 0, h = k - 1;
@@ -1029,11 +1114,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
         // the tile's upper bound (a tie with the splitter), which is not beyond c0 in an empty
         // tile (lo == hi); the second one always is
         int32_t c = RD + lay.start[i], r = lay.len[i] + 2;
-        while (r > 1) {
-          const int32_t half = r >> 1;
-          c += (sm.ldx(c + half - 1) <= cg) ? half : 0;
-          r -= half;
-        }
+        while (r > 1) search_step4(sm, c, r, cg);
         s_coarse[i * (NC + 1) + g_] = c;
         if (g_ == 0) s_coarse[i * (NC + 1) + NC] = RD + lay.start[i] + lay.len[i] + 1;
       }
@@ -1054,15 +1135,12 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
       int32_t longest = 1;
 #pragma unroll
       for (int i = 0; i < K; ++i) longest = imax(longest, rem[i]);
-      for (; longest > 1; longest -= longest >> 1) {
+      while (longest > 1) {
+        longest = 1;
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-          const int32_t half = rem[i] >> 1;
-          if (half > 0) {
-            const bool right = sm.ldx(cur[i] + half - 1) <= c0;
-            cur[i] += right ? half : 0;
-            rem[i] -= half;
-          }
+          if (rem[i] > 1) search_step4(sm, cur[i], rem[i], c0);
+          longest = imax(longest, rem[i]);
         }
       }
     }

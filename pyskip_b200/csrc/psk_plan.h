@@ -28,6 +28,8 @@ struct DView {
   uint32_t m;                   // number of selected positions
 };
 
+constexpr int kIndexStride = 16;
+
 struct DSource {
   // (end, payload) pairs, 8 bytes per run, ends strictly increasing; pairs [nruns] and
   // [nruns + 1] are sentinels (end = INT_MAX) and the allocation extends 4 pairs beyond nruns,
@@ -36,11 +38,16 @@ struct DSource {
   // run count of a source that is itself a queued (deferred) result: read on the device by
   // k_prepare; nruns then holds the capacity (an upper bound)
   const int32_t* d_count;
+  // ends of every kIndexStride-th run, compact: index[i] = runs[kIndexStride (i + 1) - 1].x for
+  // i < nruns / kIndexStride (built once per store, on first use as a source); the partition
+  // kernel reads its samples here instead of gathering them from the run array
+  const int32_t* index;
   int32_t nruns;
   int32_t nviews;
   int32_t a, e;      // raw run-index range [a, e) that can contribute to the output
+  int32_t g0;        // first sample: the first run index >= a with (index + 1) % S == 0
   int32_t ns;        // number of partition samples taken from this source
-  int32_t samp_off;  // first sample id of this source
+  int32_t blk_off;   // first block of k_partition that ranks samples of this source (blocks never mix sources)
   DView v[PSK_MAX_VIEWS];
 };
 

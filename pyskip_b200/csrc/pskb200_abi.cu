@@ -33,6 +33,8 @@ struct psk_store_s {
   int32_t span = 0;
   int2* d_runs = nullptr;       // (end, payload) pairs: capacity + kStorePad pairs; [nruns], [nruns+1] sentinels
   int32_t* d_count = nullptr;   // the run count on the device (inside the padding of d_runs)
+  int32_t* d_index = nullptr;   // ends of every kIndexStride-th run (behind the padding, same allocation)
+  bool indexed = false;         // ... filled (on first use as a source of an evaluation)
   cudaEvent_t ready = nullptr;  // produced on another stream (async upload): consumers wait for it
   cudaEvent_t busy = nullptr;   // async download finished (waited on before the memory is freed)
   int32_t pending_slot = -1;    // result of psk_eval_async whose run count has not been read yet
@@ -54,6 +56,8 @@ struct Ctx {
   cudaEvent_t pev0 = nullptr, pev1 = nullptr;  // bracket the merge/eval kernel when profiling
   bool profile = false;
   double prof_ms = 0.0;
+  bool profile_partition = false;
+  int sample_div = 32;  // sample stride S = tile capacity / sample_div (tuning aid: PSKB200_SAMPLE_DIV)
   int64_t prof_n = 0;
   int64_t prof_runs_in = 0, prof_runs_out = 0;
   unsigned long long phase_cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -177,6 +181,11 @@ psk_status do_init(int device) {
     const int c = atoi(sv);
     if (c >= 512 && c <= 13000 && c % 64 == 0) g.jit_CAP = c;
   }
+  if (const char* sv = getenv("PSKB200_PROFILE_PARTITION")) g.profile_partition = atoi(sv) != 0;
+  if (const char* sv = getenv("PSKB200_SAMPLE_DIV")) {
+    const int d = atoi(sv);
+    if (d >= 8 && d <= 128) g.sample_div = d;
+  }
   g.device = device;
   g.inited = true;
   return PSK_OK;
@@ -204,18 +213,24 @@ int elem_size(int dtype) { return (dtype == PSK_I32 || dtype == PSK_F32) ? 4 : 1
 
 constexpr int64_t kStorePad = 4;  // pairs behind the capacity: 2 sentinels, tile-load slack, the count word
 
+// one allocation per store: capacity + kStorePad pairs, then the compact index
+size_t store_bytes(int64_t capacity) {
+  return (size_t)(capacity + kStorePad) * 8 + (size_t)(capacity / kIndexStride + 1) * 4;
+}
+
 psk_status new_store(int dtype, int64_t capacity, psk_store_t* out) {
   psk_store_s* s = new (std::nothrow) psk_store_s();
   if (!s) return fail(PSK_ENOMEM, "out of host memory");
   s->dtype = dtype;
   s->capacity = capacity;
-  psk_status st = dmalloc(reinterpret_cast<void**>(&s->d_runs), (size_t)(capacity + kStorePad) * 8);
+  psk_status st = dmalloc(reinterpret_cast<void**>(&s->d_runs), store_bytes(capacity));
   if (st != PSK_OK) {
     delete s;
     return st;
   }
   // the last padding pair holds the run count for device-side consumers (queued results)
   s->d_count = reinterpret_cast<int32_t*>(s->d_runs + capacity + kStorePad - 1);
+  s->d_index = reinterpret_cast<int32_t*>(s->d_runs + capacity + kStorePad);
   g.live_bytes += capacity * 8;
   *out = s;
   return PSK_OK;
@@ -233,7 +248,7 @@ void wait_ready(psk_store_s* s) {
 void right_size(psk_store_s* s) {
   if (s->nruns <= 0 || s->capacity < 4096 || s->capacity <= 2 * s->nruns) return;
   int2* small = nullptr;
-  if (cudaMallocAsync(reinterpret_cast<void**>(&small), (size_t)(s->nruns + kStorePad) * 8, g.stream) != cudaSuccess) {
+  if (cudaMallocAsync(reinterpret_cast<void**>(&small), store_bytes(s->nruns), g.stream) != cudaSuccess) {
     cudaGetLastError();
     return;
   }
@@ -245,6 +260,8 @@ void right_size(psk_store_s* s) {
   g.live_bytes -= (s->capacity - s->nruns) * 8;
   s->d_runs = small;
   s->d_count = new_count;
+  s->d_index = reinterpret_cast<int32_t*>(small + s->nruns + kStorePad);
+  s->indexed = false;
   s->capacity = s->nruns;
 }
 
@@ -395,6 +412,13 @@ __global__ void k_boundary(const int2* runs, int64_t nruns, const int32_t* d_cou
     out3[1] = (long long)(uint32_t)runs[nruns - 1].y;
     out3[2] = (long long)nruns;
   }
+}
+
+// index[i] = end of run kIndexStride (i + 1) - 1  (see DSource::index)
+__global__ void k_build_index(const int2* runs, int32_t nruns, const int32_t* d_count, int32_t* index) {
+  const int32_t n = d_count ? ld_nc(d_count) : nruns;
+  const int32_t i = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (i < n / kIndexStride) index[i] = ld_nc(runs + (kIndexStride * (i + 1) - 1)).x;
 }
 
 __global__ void k_fill_one(int2* runs, int32_t* d_count, int32_t span, uint32_t bits) {
@@ -1129,6 +1153,13 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
       wait_ready(s.store);
       used_async = true;
     }
+    if (!s.store->indexed && d.nruns >= kIndexStride) {  // first use as a source: build the compact index
+      const int32_t entries = d.nruns / kIndexStride;
+      LAUNCH(k_build_index, (unsigned)((entries + 255) / 256), 256, 0, (const int2*)s.store->d_runs, d.nruns,
+             (const int32_t*)d.d_count, s.store->d_index);
+      s.store->indexed = true;
+    }
+    d.index = s.store->d_index;
     // every source of a pool must share the output span (eval.hpp:400-403, lang.hpp:198)
     if (span < 0) span = cur;
     else if (span != cur) return fail(PSK_EINVAL, "sources have different spans");
@@ -1160,14 +1191,16 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
   if (ctas > 2048 / T) ctas = 2048 / T;
   if (ctas < 1) ctas = 1;
 
-  // ---- partition parameters: S * (m + 2k) <= CAP bounds the runs of one tile ---------------
-  int S = CAP / 32;
-  if (k > 8) S = CAP / 64;
+  // ---- partition parameters: S * (m + k) <= CAP bounds the runs of one tile ---------------
+  // (a tile holds m samples; source q with c_q of them contributes at most (c_q + 1) S - 1 runs)
+  int S = CAP / g.sample_div;
+  if (k > 8) S = CAP / (2 * g.sample_div);
   while (S > 16 && total_runs / S < 1024) S >>= 1;
-  while (S > 4 && CAP / S - 2 * k < 4) S >>= 1;
+  while (S > 4 && CAP / S - k < 4) S >>= 1;
+  if (S >= kIndexStride) S -= S % kIndexStride;  // samples on the grid of the stores' compact index
   int64_t max_samples = 0;
-  for (int i = 0; i < k; ++i) max_samples += (hp.src[i].nruns + S - 1) / S;
-  const int m_max = CAP / S - 2 * k;
+  for (int i = 0; i < k; ++i) max_samples += hp.src[i].nruns / S + 2;  // (a source trimmed on the device: its first interval is short)
+  const int m_max = CAP / S - k;
   int m = (int)(max_samples / (2 * (int64_t)ctas * g.sm_count));  // aim at >= 2 tiles per resident CTA ...
   const int m_small = (CAP / 4) / S;                              // ... but not at tiles below CAP/4 runs
   if (m < m_small) m = m_small;
@@ -1178,13 +1211,15 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
   hp.m = m;
   hp.max_tiles = (int32_t)max_tiles;
   {
-    int32_t off = 0;
+    int32_t off = 0, blk = 0;
     for (int i = 0; i < k; ++i) {
       DSource& d = hp.src[i];
       d.a = 0;
       d.e = d.nruns;
-      d.ns = (d.nruns + S - 1) / S;
-      d.samp_off = off;
+      d.g0 = first_sample(0, S);
+      d.ns = sample_count(0, d.nruns, S);
+      d.blk_off = blk;
+      blk += (d.ns + kPartBlock - 1) / kPartBlock;
       off += d.ns;
     }
     hp.total_samples = off;
@@ -1236,10 +1271,14 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
 #endif
   if (e == cudaSuccess) {
     if (on_device) LAUNCH(k_prepare, 1, 32 * k, 0, d_plan);
-    int64_t pgrid = (max_samples + kPartBlock - 1) / kPartBlock;
-    if (pgrid < 1) pgrid = 1;
+    int64_t pgrid = 0;  // one source per block; a source trimmed on the device has at most nruns / S + 2 samples
+    for (int i = 0; i < k; ++i) pgrid += (hp.src[i].nruns / S + 2 + kPartBlock - 1) / kPartBlock;
+    // (development: PSKB200_PROFILE_PARTITION=1 makes the profile events bracket k_partition)
+    if (g.profile && g.profile_partition) cudaEventRecord(deferred ? g.slots[slot].t0 : g.pev0, g.stream);
     LAUNCH(k_partition, (unsigned)pgrid, kPartBlock, 0, d_plan);
-    if (g.profile) cudaEventRecord(deferred ? g.slots[slot].t0 : g.pev0, g.stream);
+    if (g.profile)
+      cudaEventRecord(deferred ? (g.profile_partition ? g.slots[slot].t1 : g.slots[slot].t0)
+                               : (g.profile_partition ? g.pev1 : g.pev0), g.stream);
     bool launched = false;
 #ifndef PSK_CPU_SIM
     if (jk) {
@@ -1253,7 +1292,7 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
     }
 #endif
     if (!launched && e == cudaSuccess) launch_merge_eval(pick_K(k), (int)grid, d_plan);
-    if (g.profile) cudaEventRecord(deferred ? g.slots[slot].t1 : g.pev1, g.stream);
+    if (g.profile && !g.profile_partition) cudaEventRecord(deferred ? g.slots[slot].t1 : g.pev1, g.stream);
     if (deferred) {
       g.slots[slot].timed = g.profile;
       g.slots[slot].runs_in = total_runs;

@@ -20,9 +20,14 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--geoms", default="128x4096,64x2048,128x2048,256x4096,256x8192,192x6144,64x4096,96x3072")
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--lib", default="", help="path of a library variant (default: the package's)")
     args = ap.parse_args()
     from pyskip_b200 import _abi as A
-    lib = A.lib()
+    if args.lib:
+        lib = A.Lib(args.lib)
+        lib.init(0)
+    else:
+        lib = A.lib()
     assert not lib.is_simulator()
     n_elems, n_runs = int(bench.N_ELEMS * args.scale), int(bench.N_RUNS * args.scale)
     t0 = time.time()
