@@ -137,13 +137,10 @@ __global__ void __launch_bounds__(kConvThreads) k_encode_write(const void* dense
 }
 
 // ---------------------------------------------------------------------------------------
-// Vectorised forms for 4-byte element types and 16-byte aligned dense buffers
-// (selected at run time by psk_set_vector_conversion; off by default until measured on the
-// GPU -- the scalar kernels above reach 12-19 % of the HBM peak, profiles/r1_summary.md).
-// Every thread moves 16 bytes per access; a vector's right neighbour comes from the next
-// lane by shuffle.
-constexpr int kVecItems = 8;                              // 16-byte vectors per thread
-constexpr int kVecChunk = kConvThreads * 4 * kVecItems;   // dense elements per block
+// Streaming forms for 4-byte element types and 16-byte aligned dense buffers (the default;
+// psk_set_vector_conversion(0) selects the scalar kernels above, which also serve the 1-byte
+// types).  Every thread moves 16 bytes per access; a vector's right neighbour comes from the
+// next lane by shuffle.
 
 // elements [i, i + 4) of a 4-byte dense buffer (i a multiple of 4; elements beyond n read 0)
 PSK_D uint4 load_vec4(const void* dense, long long i, long long n) {
@@ -157,11 +154,11 @@ PSK_D uint4 load_vec4(const void* dense, long long i, long long n) {
 }
 
 // bit j set: element i + j exists and closes a run (last element, or differs from i + j + 1)
+// (edge: the element behind the warp's 32 vectors, loaded by lane 31 together with the vectors)
 template <int DT>
-PSK_D unsigned close_flags4(const void* dense, long long i, long long n, const uint4& v) {
-  // first element of the vector to the right: the next lane holds it, lane 31 loads it
+PSK_D unsigned close_flags4_edge(long long i, long long n, const uint4& v, uint32_t edge) {
   uint32_t nx = __shfl_down_sync(0xffffffffu, v.x, 1);
-  if ((threadIdx.x & 31) == 31 && i + 4 < n) nx = reinterpret_cast<const uint32_t*>(dense)[i + 4];
+  if ((threadIdx.x & 31) == 31) nx = edge;
   unsigned f = 0;
   if (i < n && (i == n - 1 || typed_differs<DT>(v.x, v.y))) f |= 1u;
   if (i + 1 < n && (i + 1 == n - 1 || typed_differs<DT>(v.y, v.z))) f |= 2u;
@@ -170,45 +167,89 @@ PSK_D unsigned close_flags4(const void* dense, long long i, long long n, const u
   return f;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// One-pass encode (4-byte elements, 16-byte aligned buffer): the dense buffer is read ONCE.
+// Block b encodes chunk b (kEncChunk elements): it counts the runs it closes, gets its output
+// offset by a decoupled look-back over the chunks in front of it (one warp polls a window of
+// 32 predecessors; status and count travel in one 64-bit word) and writes its runs.  Chunks are
+// taken in blockIdx order -- blocks of a 1-D grid are dispatched in that order, so every
+// predecessor of a running block is running or done (the assumption of CUB's DeviceScan).
+// The output is allocated for `capacity` runs; runs beyond it are counted but not written and
+// the caller repeats the pass with the exact size (dense data only).
+constexpr unsigned long long kEncAggregate = 1ull, kEncPrefix = 2ull;
+#ifndef PSK_ENC_LOOK
+#define PSK_ENC_LOOK 8
+#endif
+#ifndef PSK_ENC_ITEMS
+#define PSK_ENC_ITEMS 8
+#endif
+#ifndef PSK_ENC_MINBLOCKS
+#define PSK_ENC_MINBLOCKS 2
+#endif
+constexpr int kEncLook = PSK_ENC_LOOK;                                 // look-back: kEncLook windows of 32 chunks per round
+constexpr int kEncStride = 4;                               // 64-bit words per look-back entry (one 32-byte sector each)
+#ifndef PSK_ENC_THREADS
+#define PSK_ENC_THREADS 512
+#endif
+constexpr int kEncThreads = PSK_ENC_THREADS;
+constexpr int kEncItems = PSK_ENC_ITEMS;                                // 16-byte vectors per thread
+constexpr int kEncChunk = kEncThreads * 4 * kEncItems;     // dense elements per block
+
+// bit j set: element j of the vector closes a run; `full`: the vector and its right neighbour exist
 template <int DT>
-__global__ void __launch_bounds__(kConvThreads) k_encode_count_vec(const void* dense, long long n,
-                                                                   int32_t* block_count) {
-  __shared__ int32_t s_warp[kConvThreads / 32];
-  const long long base = (long long)blockIdx.x * kVecChunk;
-  int32_t c = 0;
-#pragma unroll
-  for (int it = 0; it < kVecItems; ++it) {
-    const long long i = base + ((long long)it * kConvThreads + threadIdx.x) * 4;
-    const uint4 v = load_vec4(dense, i, n);
-    c += __popc(close_flags4<DT>(dense, i, n, v));
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
-  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int32_t t = 0;
-    for (int w = 0; w < kConvThreads / 32; ++w) t += s_warp[w];
-    block_count[blockIdx.x] = t;
-  }
+PSK_D unsigned close_flags4_fast(const uint4& v, uint32_t edge) {
+  uint32_t nx = __shfl_down_sync(0xffffffffu, v.x, 1);
+  if ((threadIdx.x & 31) == 31) nx = edge;
+  return (typed_differs<DT>(v.x, v.y) ? 1u : 0u) | (typed_differs<DT>(v.y, v.z) ? 2u : 0u) |
+         (typed_differs<DT>(v.z, v.w) ? 4u : 0u) | (typed_differs<DT>(v.w, nx) ? 8u : 0u);
 }
 
 template <int DT>
-__global__ void __launch_bounds__(kConvThreads) k_encode_write_vec(const void* dense, long long n,
-                                                                   const int32_t* block_off,
-                                                                   int2* runs) {
-  constexpr int W = kConvThreads / 32;
-  __shared__ int32_t s_tot[kVecItems][W];  // runs closed by warp w in item it
-  const long long base = (long long)blockIdx.x * kVecChunk;
+__global__ void __launch_bounds__(kEncThreads, PSK_ENC_MINBLOCKS) k_encode_onepass(const void* dense, long long n, int32_t nb,
+                                                                    unsigned long long* state, int32_t* total_out,
+                                                                    int2* runs, int32_t capacity) {
+  constexpr int W = kEncThreads / 32;
+  __shared__ int32_t s_tot[kEncItems * W + 1];  // runs closed by warp w in item it; then their exclusive offsets
+  __shared__ int32_t s_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint4 v[kVecItems];
-  unsigned f[kVecItems];
-  int32_t before[kVecItems];  // runs closed by lower lanes of this warp in the same item
+  const int32_t tile = (int32_t)blockIdx.x;
+  const long long base = (long long)tile * kEncChunk;
+  const bool interior = base + kEncChunk + 4 <= n;  // no bounds tests needed (and no last element here)
+  // Only the flags stay in registers: the payloads of the (few) elements that close a run are
+  // read again from the cache when the runs are written, which keeps enough blocks resident
+  // to cover the look-back with other blocks' loads.
+  unsigned f[kEncItems];
+  int32_t before[kEncItems];  // runs closed by lower lanes of this warp in the same item
+  const uint32_t* const p32 = reinterpret_cast<const uint32_t*>(dense);
+  {
+    uint4 v[kEncItems];
+    uint32_t edge[kEncItems];  // lane 31: the element behind the warp's vectors (all loads issued up front)
+    if (interior) {
 #pragma unroll
-  for (int it = 0; it < kVecItems; ++it) {
-    const long long i = base + ((long long)it * kConvThreads + threadIdx.x) * 4;
-    v[it] = load_vec4(dense, i, n);
-    f[it] = close_flags4<DT>(dense, i, n, v[it]);
+      for (int it = 0; it < kEncItems; ++it) {
+        const long long i = base + ((long long)it * kEncThreads + threadIdx.x) * 4;
+        v[it] = *reinterpret_cast<const uint4*>(p32 + i);
+        edge[it] = lane == 31 ? p32[i + 4] : 0u;
+      }
+#pragma unroll
+      for (int it = 0; it < kEncItems; ++it) f[it] = close_flags4_fast<DT>(v[it], edge[it]);
+    } else {
+#pragma unroll
+      for (int it = 0; it < kEncItems; ++it) {
+        const long long i = base + ((long long)it * kEncThreads + threadIdx.x) * 4;
+        v[it] = load_vec4(dense, i, n);
+        edge[it] = (lane == 31 && i + 4 < n) ? p32[i + 4] : 0u;
+      }
+#pragma unroll
+      for (int it = 0; it < kEncItems; ++it) {
+        const long long i = base + ((long long)it * kEncThreads + threadIdx.x) * 4;
+        f[it] = close_flags4_edge<DT>(i, n, v[it], edge[it]);
+      }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < kEncItems; ++it) {
     const int32_t c = __popc(f[it]);
     int32_t inc = c;
 #pragma unroll
@@ -217,83 +258,203 @@ __global__ void __launch_bounds__(kConvThreads) k_encode_write_vec(const void* d
       if (lane >= d) inc += o;
     }
     before[it] = inc - c;
-    if (lane == 31) s_tot[it][warp] = inc;
+    if (lane == 31) s_tot[it * W + warp] = inc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // exclusive offsets of the (item, warp) pieces in output order, the chunk's run count, the look-back
+    constexpr int kPieces = kEncItems * W, kPer = (kPieces + 31) / 32;  // consecutive pieces per lane
+    int32_t c[kPer], sum = 0;
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      c[u] = lane * kPer + u < kPieces ? s_tot[lane * kPer + u] : 0;
+      sum += c[u];
+    }
+    int32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    const int32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    int32_t run = inc - sum;
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      if (lane * kPer + u < kPieces) s_tot[lane * kPer + u] = run;
+      run += c[u];
+    }
+    int32_t excl = 0;
+    if (tile == 0) {
+      if (lane == 0) st_volatile_u64(&state[0], (kEncPrefix << 32) | (uint32_t)total);
+    } else {
+      if (lane == 0) st_volatile_u64(&state[(long long)tile * kEncStride], (kEncAggregate << 32) | (uint32_t)total);
+      // kEncLook windows of 32 predecessors are requested together (one memory round trip) and
+      // folded from the nearest one outwards; a window with a chunk that has not published yet is
+      // polled again on its own.  The rate at which chunks can resolve their offsets is about
+      // (window * chunk bytes) per round trip, so the window has to be wide: the blocks of a wave
+      // start together and the nearest inclusive prefix is often a whole wave away.
+      int32_t idx = tile - 1;
+      bool done = false;
+      while (!done) {
+        unsigned long long w[kEncLook];
+#pragma unroll
+        for (int u = 0; u < kEncLook; ++u) {
+          const int32_t my = idx - (u * 32 + lane);
+          w[u] = my >= 0 ? ld_volatile_u64(&state[(long long)my * kEncStride]) : (kEncPrefix << 32);
+        }
+#pragma unroll
+        for (int u = 0; u < kEncLook; ++u) {
+          if (done) continue;
+          while (true) {
+            const unsigned st = (unsigned)(w[u] >> 32);
+            const unsigned empty = __ballot_sync(0xffffffffu, st == 0u);
+            const unsigned pre = __ballot_sync(0xffffffffu, st == (unsigned)kEncPrefix);
+            const int first_pre = pre ? __ffs((int)pre) - 1 : 32;  // nearest chunk with an inclusive prefix
+            const unsigned need = first_pre >= 31 ? 0xffffffffu : ((2u << first_pre) - 1u);
+            if ((empty & need) == 0u) {
+              int32_t part = lane <= first_pre ? (int32_t)(uint32_t)w[u] : 0;
+#pragma unroll
+              for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+              excl += part;
+              if (first_pre < 32) done = true;
+              break;
+            }
+            sleep_ns(64);  // a chunk in between has not published yet
+            const int32_t my = idx - (u * 32 + lane);
+            w[u] = my >= 0 ? ld_volatile_u64(&state[(long long)my * kEncStride]) : (kEncPrefix << 32);
+          }
+        }
+        idx -= kEncLook * 32;
+      }
+      if (lane == 0) st_volatile_u64(&state[(long long)tile * kEncStride], (kEncPrefix << 32) | (uint32_t)(excl + total));
+    }
+    if (lane == 0) {
+      s_base = excl;
+      if (tile == nb - 1) *total_out = excl + total;
+    }
   }
   __syncthreads();
   // output order = element order: items, then warps, then lanes, then the 4 elements
-  int32_t pos = block_off[blockIdx.x];
+  const int32_t pos = s_base;
 #pragma unroll
-  for (int it = 0; it < kVecItems; ++it) {
-    int32_t mine = pos + before[it];
-    int32_t tot = 0;
-#pragma unroll
-    for (int w = 0; w < W; ++w) {
-      const int32_t c = s_tot[it][w];
-      if (w < warp) mine += c;
-      tot += c;
-    }
-    const long long i = base + ((long long)it * kConvThreads + threadIdx.x) * 4;
-    const uint32_t x[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+  for (int it = 0; it < kEncItems; ++it) {
+    int32_t mine = pos + s_tot[it * W + warp] + before[it];
+    const long long i = base + ((long long)it * kEncThreads + threadIdx.x) * 4;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (f[it] & (1u << j)) {
-        runs[mine] = make_int2((int32_t)(i + j + 1), (int32_t)x[j]);
+        if (mine < capacity) runs[mine] = make_int2((int32_t)(i + j) + 1, (int32_t)p32[i + j]);
         ++mine;
       }
     }
-    pos += tot;
   }
 }
 
-// expand, 4 consecutive elements per thread and access: one search, then a linear advance;
-// the chunk's run values are staged next to its ends
+// ---------------------------------------------------------------------------------------
+// Streaming expand (4-byte elements, 16-byte aligned buffer), two kernels:
+//   k_expand_table   first run of every chunk of kExpChunk elements (one search per chunk, all
+//                    chunks at once);
+//   k_expand_chunks  a persistent grid walks the chunks in grid-stride order (the chunks being
+//                    written at any time are neighbours in memory): stage the chunk's runs, find
+//                    the run of every 4-element group in shared memory, store 16 bytes per thread.
+constexpr int kExpChunk = kConvThreads * 8;  // dense elements per chunk (a chunk has at most kExpChunk + 1 runs)
+
+__global__ void k_expand_table(const int2* runs, int32_t nruns, int32_t nchunks, int32_t* table /*[nchunks + 1]*/) {
+  const int32_t c = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (c > nchunks) return;
+  if (c == nchunks) {
+    table[c] = nruns - 1;
+    return;
+  }
+  // first run whose end is > c * kExpChunk (core::Store::index, core.hpp:49-52)
+  const int32_t pos = c * kExpChunk;
+  int32_t lo = 0, hi = nruns;
+  while (lo < hi) {
+    const int32_t mid = lo + ((hi - lo) >> 1);
+    if (ld_nc(runs + mid).x <= pos) lo = mid + 1; else hi = mid;
+  }
+  table[c] = lo;
+}
+
 template <int DT>
-__global__ void __launch_bounds__(kConvThreads) k_expand_vec(const int2* runs,
-                                                             int32_t nruns, long long n, void* dense) {
-  __shared__ int32_t s_ends[kConvChunk + 1];
-  __shared__ uint32_t s_vals[kConvChunk + 1];
-  __shared__ int32_t s_r0, s_nr;
-  const long long b0 = (long long)blockIdx.x * kConvChunk;
-  long long b1 = b0 + kConvChunk;
-  if (b1 > n) b1 = n;
-  if (threadIdx.x < 2) {
-    int32_t pos = threadIdx.x == 0 ? (int32_t)b0 : (int32_t)(b1 - 1);
-    int32_t lo = 0, hi = nruns;
-    while (lo < hi) {
-      int32_t mid = lo + ((hi - lo) >> 1);
-      if (runs[mid].x <= pos) lo = mid + 1; else hi = mid;
-    }
-    if (threadIdx.x == 0) s_r0 = lo; else s_nr = lo;
-  }
-  __syncthreads();
-  const int32_t r0 = s_r0;
-  const int32_t nr = s_nr - r0 + 1;
-  for (int32_t j = threadIdx.x; j < nr; j += kConvThreads) {
-    const int2 r = runs[r0 + j];
-    s_ends[j] = r.x;
-    s_vals[j] = (uint32_t)r.y;
-  }
-  __syncthreads();
+__global__ void __launch_bounds__(kConvThreads) k_expand_chunks(const int2* runs, int32_t nruns, long long n,
+                                                                const int32_t* table, int32_t nchunks, void* dense) {
+  constexpr int kWords = kExpChunk / 32;
+  __shared__ uint32_t s_vals[kExpChunk + 2];
+  __shared__ uint32_t s_bits[kWords];   // bit x: element b0 + x is the last one of its run
+  __shared__ int32_t s_pref[kWords];    // runs that end in front of word w
   uint32_t* const out = reinterpret_cast<uint32_t*>(dense);
-  for (int it = 0; it < kConvItems / 4; ++it) {
-    const long long i = b0 + ((long long)it * kConvThreads + threadIdx.x) * 4;
-    if (i >= b1) continue;
-    int32_t lo = 0, hi = nr - 1;  // run of element i
-    while (lo < hi) {
-      int32_t mid = (lo + hi) >> 1;
-      if (s_ends[mid] <= (int32_t)i) lo = mid + 1; else hi = mid;
+  int32_t c = (int32_t)blockIdx.x;
+  if (c >= nchunks) return;
+  int32_t r0 = ld_nc(table + c), r1 = ld_nc(table + c + 1);
+  for (; c < nchunks; c += (int32_t)gridDim.x) {
+    const long long b0 = (long long)c * kExpChunk;
+    const long long b1 = b0 + kExpChunk < n ? b0 + kExpChunk : n;
+    if (threadIdx.x < kWords) s_bits[threadIdx.x] = 0u;
+    __syncthreads();
+    // runs r0 .. r1 cover the chunk (r1 = first run of the next chunk; it may reach into this one)
+    const int32_t nr = r1 - r0 + 1;
+    for (int32_t j = threadIdx.x; j < nr; j += kConvThreads) {
+      const int2 pr = ld_nc(runs + r0 + j);
+      s_vals[j] = (uint32_t)pr.y;
+      const long long last = (long long)pr.x - 1 - b0;  // the run's last element, relative to the chunk
+      if (last < (long long)kExpChunk) atomicOr(&s_bits[last >> 5], 1u << (last & 31));
     }
-    uint32_t x[4];
+    // the next chunk's table entries, in flight while this chunk is written
+    const int32_t cn = c + (int32_t)gridDim.x;
+    int32_t nr0 = 0, nr1 = 0;
+    if (cn < nchunks) {
+      nr0 = ld_nc(table + cn);
+      nr1 = ld_nc(table + cn + 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {  // exclusive prefix of the words' bit counts (kWords = 64: two per lane)
+      static_assert(kWords == 64, "two words per lane");
+      const int32_t c0 = __popc(s_bits[2 * threadIdx.x]), c1 = __popc(s_bits[2 * threadIdx.x + 1]);
+      int32_t inc = c0 + c1;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      while (lo < nr - 1 && s_ends[lo] <= (int32_t)(i + j)) ++lo;
-      x[j] = s_vals[lo];
+      for (int d = 1; d < 32; d <<= 1) {
+        const int32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if ((int)threadIdx.x >= d) inc += o;
+      }
+      s_pref[2 * threadIdx.x] = inc - c0 - c1;
+      s_pref[2 * threadIdx.x + 1] = inc - c1;
     }
-    if (i + 3 < b1) {
-      *reinterpret_cast<uint4*>(out + i) = make_uint4(x[0], x[1], x[2], x[3]);
-    } else {
-      for (int j = 0; j < 4 && i + j < b1; ++j) out[i + j] = x[j];
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kExpChunk / (kConvThreads * 4); ++it) {
+      const int32_t x = (it * kConvThreads + (int)threadIdx.x) * 4;  // offset in the chunk
+      const long long i = b0 + x;
+      if (i >= b1) continue;
+      // run of element x (relative to r0) = number of runs that end in front of it
+      const uint32_t word = s_bits[x >> 5];
+      const int bit = x & 31;
+      int32_t k0 = s_pref[x >> 5] + __popc(word & ((1u << bit) - 1u));
+      const uint32_t nib = (word >> bit) & 7u;  // elements x, x+1, x+2 that end a run
+      uint4 o;
+      o.x = s_vals[k0];
+      if (nib == 0u) {
+        o.y = o.z = o.w = o.x;
+      } else {
+        k0 += nib & 1u;
+        o.y = s_vals[k0];
+        k0 += (nib >> 1) & 1u;
+        o.z = s_vals[k0];
+        k0 += (nib >> 2) & 1u;
+        o.w = s_vals[k0];
+      }
+      if (i + 3 < b1) {
+        *reinterpret_cast<uint4*>(out + i) = o;
+      } else {
+        const uint32_t xs[4] = {o.x, o.y, o.z, o.w};
+        for (int j = 0; j < 4 && i + j < b1; ++j) out[i + j] = xs[j];
+      }
     }
+    r0 = nr0;
+    r1 = nr1;
+    // (the next iteration's first barrier separates these reads from its writes of s_vals / s_pref;
+    //  s_bits is cleared before that barrier, so it needs its own)
+    __syncthreads();
   }
 }
 

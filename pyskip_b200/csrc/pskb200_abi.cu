@@ -462,12 +462,57 @@ psk_status encode_device(const void* d_dense, int64_t n, psk_store_t* out) {
   // 16-byte accesses for 4-byte elements in an aligned buffer
   const bool vec = g.convert_vec && (DT == PSK_I32 || DT == PSK_F32) &&
                    (reinterpret_cast<uintptr_t>(d_dense) & 15) == 0;
-  const int32_t nb = (int32_t)((n + (vec ? kVecChunk : kConvChunk) - 1) / (vec ? kVecChunk : kConvChunk));
+  const int32_t nb = (int32_t)((n + (vec ? kEncChunk : kConvChunk) - 1) / (vec ? kEncChunk : kConvChunk));
+  if (vec) {
+    // one pass over the buffer; the output is sized for one run per two elements and the pass is
+    // repeated with the exact size in the (dense) case that this is not enough
+    int64_t cap = n / 2 + 4096;
+    if (cap > n) cap = n;
+    unsigned char* d_scr = nullptr;
+    const size_t scr_bytes = (size_t)nb * 8 * kEncStride + 16;
+    psk_status st = dmalloc(reinterpret_cast<void**>(&d_scr), scr_bytes);
+    if (st != PSK_OK) return st;
+    psk_store_t s = nullptr;
+    int64_t nruns = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      st = new_store(DT, cap, &s);
+      if (st != PSK_OK) break;
+      cudaMemsetAsync(d_scr, 0, scr_bytes, g.stream);
+      int32_t* ctl = reinterpret_cast<int32_t*>(d_scr + (size_t)nb * 8 * kEncStride);
+      LAUNCH(k_encode_onepass<DT>, nb, kEncThreads, 0, d_dense, (long long)n, nb,
+             reinterpret_cast<unsigned long long*>(d_scr), ctl, s->d_runs, (int32_t)cap);
+      cudaError_t e = cudaMemcpyAsync(g.h_ctrl, ctl, 4, cudaMemcpyDeviceToHost, g.stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+      if (e != cudaSuccess) {
+        st = fail(PSK_ECUDA, std::string("psk_store_from_dense: ") + cudaGetErrorString(e));
+        break;
+      }
+      nruns = g.h_ctrl[0];
+      if (nruns <= cap) break;
+      psk_store_release(s);
+      s = nullptr;
+      cap = nruns;
+    }
+    cudaFreeAsync(d_scr, g.stream);
+    if (st != PSK_OK) {
+      if (s) psk_store_release(s);
+      return st;
+    }
+    if (nruns <= 0) {
+      psk_store_release(s);
+      return fail(PSK_ESTATE, "psk_store_from_dense: produced no runs");
+    }
+    LAUNCH(k_seal, 1, 32, 0, s->d_runs, (int32_t)nruns, s->d_count);
+    s->nruns = nruns;
+    s->span = (int32_t)n;
+    right_size(s);
+    *out = s;
+    return PSK_OK;
+  }
   int32_t* d_counts = nullptr;
   psk_status st = dmalloc(reinterpret_cast<void**>(&d_counts), (size_t)(nb + 1) * 4);
   if (st != PSK_OK) return st;
-  if (vec) LAUNCH(k_encode_count_vec<DT>, nb, kConvThreads, 0, d_dense, (long long)n, d_counts);
-  else LAUNCH(k_encode_count<DT>, nb, kConvThreads, 0, d_dense, (long long)n, d_counts);
+  LAUNCH(k_encode_count<DT>, nb, kConvThreads, 0, d_dense, (long long)n, d_counts);
   LAUNCH(k_scan_counts, 1, 1024, 0, d_counts, nb, d_counts + nb);
   CUDA_TRY(cudaMemcpyAsync(g.h_ctrl, d_counts + nb, 4, cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
@@ -479,8 +524,7 @@ psk_status encode_device(const void* d_dense, int64_t n, psk_store_t* out) {
     cudaFreeAsync(d_counts, g.stream);
     return st;
   }
-  if (vec) LAUNCH(k_encode_write_vec<DT>, nb, kConvThreads, 0, d_dense, (long long)n, d_counts, s->d_runs);
-  else LAUNCH(k_encode_write<DT>, nb, kConvThreads, 0, d_dense, (long long)n, d_counts, s->d_runs);
+  LAUNCH(k_encode_write<DT>, nb, kConvThreads, 0, d_dense, (long long)n, d_counts, s->d_runs);
   LAUNCH(k_seal, 1, 32, 0, s->d_runs, (int32_t)nruns, s->d_count);
   CUDA_TRY(cudaFreeAsync(d_counts, g.stream));
   s->nruns = nruns;
@@ -943,8 +987,21 @@ psk_status psk_store_to_dense_device(psk_store_t s, void* d_out) {
   const unsigned nb = (unsigned)((n + kConvChunk - 1) / kConvChunk);
   if (g.convert_vec && (s->dtype == PSK_I32 || s->dtype == PSK_F32) &&
       (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {
-    // same block geometry, 16-byte stores (the two 4-byte types share the payload path)
-    LAUNCH(k_expand_vec<PSK_I32>, nb, kConvThreads, 0, s->d_runs, (int32_t)s->nruns, n, d_out);
+    // persistent grid, 16-byte stores (the two 4-byte types share the payload path)
+    const int32_t nchunks = (int32_t)((n + kExpChunk - 1) / kExpChunk);
+    int32_t* d_table = nullptr;
+    psk_status st = dmalloc(reinterpret_cast<void**>(&d_table), (size_t)(nchunks + 1) * 4);
+    if (st != PSK_OK) return st;
+    LAUNCH(k_expand_table, (unsigned)((nchunks + 1 + 255) / 256), 256, 0, (const int2*)s->d_runs, (int32_t)s->nruns, nchunks,
+           d_table);
+    long long grid = (long long)g.sm_count * 8;
+#ifdef PSK_CPU_SIM
+    grid = 3;  // (so that the simulator's small cases walk several chunks per block)
+#endif
+    if (grid > nchunks) grid = nchunks;
+    LAUNCH(k_expand_chunks<PSK_I32>, (unsigned)grid, kConvThreads, 0, (const int2*)s->d_runs, (int32_t)s->nruns, n,
+           (const int32_t*)d_table, nchunks, d_out);
+    cudaFreeAsync(d_table, g.stream);
     CUDA_TRY(cudaGetLastError());
     return PSK_OK;
   }

@@ -359,4 +359,28 @@ def test_vector_conversion_kernels_match_scalar(lib):
                 (x.dtype == np.float32 and np.array_equal(np.isnan(back), np.isnan(x))
                  and np.array_equal(back[~np.isnan(x)], x[~np.isnan(x)]))
     finally:
-        lib.set_vector_conversion(False)
+        lib.set_vector_conversion(True)   # the default
+
+
+@pytest.mark.gpu
+def test_streaming_conversion_of_a_long_buffer(lib):
+    """One-pass encode and streaming expand on a buffer long enough that every block of the
+    persistent expand kernel walks several chunks: sparse stretches, a stretch where every element
+    is its own run (more than one staging batch per chunk) and a long constant tail."""
+    if lib.is_simulator():
+        pytest.skip("sized for the GPU")
+    rng = np.random.default_rng(81)
+    n = 12_000_000
+    x = np.repeat(rng.integers(0, 50, n // 200).astype(np.int32), 200)
+    x[1_000_000:1_300_000] = np.arange(300_000, dtype=np.int32)
+    x[5_000_000:5_400_000] = np.repeat(np.arange(200_000, dtype=np.int32), 2)
+    x[9_000_000:] = 3
+    s = lib.store_from_dense(x)
+    e, v = s.runs()
+    we, wv = O.to_store(x)
+    assert_runs_equal((e, v), (we, wv.astype(np.int32)), "encode")
+    assert np.array_equal(s.to_dense(), x)
+    # dense enough that the first pass overflows its output and is repeated
+    y = np.arange(3_000_000, dtype=np.int32)
+    s = lib.store_from_dense(y)
+    assert s.nruns == y.size and np.array_equal(s.to_dense(), y)

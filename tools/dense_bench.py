@@ -16,7 +16,7 @@ import torch
 from pyskip_b200 import _abi as A
 from test_full_size import _terrain
 
-lib = A.lib()
+lib = A.Lib(os.environ["PSKB200_LIB"]) if os.environ.get("PSKB200_LIB") else A.lib()   # (a variant built by tools/build_variant.py)
 lib.init(0)
 if "--vec" in sys.argv:      # the 16-byte kernels (psk_set_vector_conversion); default: the scalar ones
     lib.set_vector_conversion(True)
