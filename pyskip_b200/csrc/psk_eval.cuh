@@ -67,6 +67,9 @@ constexpr int kParkDepth = PSK_PARK_DEPTH;
 constexpr unsigned kMergeEvalSmemBytes = (unsigned)kTileRegions * kTileRegion * 8u;
 // CTAs that stay resident per SM (227 KB of shared memory, 2048 threads)
 constexpr int kCtasBySmem = (227 * 1024) / (int)(kMergeEvalSmemBytes + 6144);
+#ifndef PSK_COARSE_GROUP
+#define PSK_COARSE_GROUP 0
+#endif
 constexpr int kCtasByThreads = 2048 / kTileThreads;
 constexpr int kCtasPerSm = kCtasBySmem < kCtasByThreads ? (kCtasBySmem < 1 ? 1 : kCtasBySmem) : kCtasByThreads;
 
@@ -875,7 +878,9 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
   __shared__ int32_t s_lbsum[LookW<T>::value * (T / 32)];
   __shared__ int32_t s_lbhas[LookW<T>::value * (T / 32)];
   __shared__ int32_t s_newstart[PSK_MAX_SOURCES];
-  __shared__ int32_t s_coarse[K * (T / 8 + 1)];  // cursors of every 8th thread
+  // cursors of every kCoarse-th thread (first level of the cursor search)
+  constexpr int kCoarse = PSK_COARSE_GROUP > 0 ? PSK_COARSE_GROUP : 8;
+  __shared__ int32_t s_coarse[K * (T / kCoarse + 1)];
   __shared__ psk_mbar_t s_bar;
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -1105,7 +1110,7 @@ PSK_D void merge_eval_tile_loop(DPlan* p, const Eval& ev) {
     int32_t cur[K], head[K], rem[K];
     uint32_t val[K];
     int32_t base = 0;
-    constexpr int CG = 8, NC = T / CG;
+    constexpr int CG = kCoarse, NC = T / CG;
     if (!fail) {
       for (int32_t q = tid; q < NC * k; q += T) {
         const int i = q / NC, g_ = q - i * NC;

@@ -216,7 +216,10 @@ bool compile_cubin(int K, bool typed_float, bool views, int T, int CAP, int regi
   const std::string opt_t = "-DPSK_TILE_THREADS=" + std::to_string(T);
   const std::string opt_c = "-DPSK_TILE_CAP=" + std::to_string(CAP);
   const std::string opt_r = "-DPSK_PARK_DEPTH=" + std::to_string(regions);
-  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo",
+  // tuning aid: extra definitions for the kernel source, e.g. PSKB200_JIT_DEFS="-DPSK_COARSE_GROUP=2"
+  const char* extra_env = getenv("PSKB200_JIT_DEFS");
+  const std::string opt_x = (extra_env && strncmp(extra_env, "-D", 2) == 0 && !strchr(extra_env, ' ')) ? extra_env : "-DPSK_JIT";
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo", opt_x.c_str(),
 #ifdef PSK_PHASE_TIMING
                         "-DPSK_PHASE_TIMING",
 #endif

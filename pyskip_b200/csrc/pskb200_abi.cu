@@ -414,6 +414,37 @@ __global__ void k_boundary(const int2* runs, int64_t nruns, const int32_t* d_cou
   }
 }
 
+// psk_store_slice: the runs that cover [start, stop) -- out2[0] = first run whose end is > start,
+// out2[1] = first run whose end is >= stop (one warp, 32 probes per round) ...
+__global__ void k_slice_find(const int2* runs, int32_t nruns, int32_t start, int32_t stop, int32_t* out2) {
+  const int lane = threadIdx.x & 31;
+  for (int which = 0; which < 2; ++which) {
+    const int32_t key = which == 0 ? start : stop - 1;  // first run whose end is > key
+    int32_t lo = 0, hi = nruns;
+    while (hi - lo > 32) {
+      const int32_t idx = lo + (int32_t)(((long long)(hi - lo) * (lane + 1)) / 33);
+      const bool before = ld_nc(runs + idx).x <= key;
+      const int nb = __popc(__ballot_sync(0xffffffffu, before));
+      const int32_t last_before = __shfl_sync(0xffffffffu, idx, nb > 0 ? nb - 1 : 0);
+      const int32_t first_after = __shfl_sync(0xffffffffu, idx, nb < 32 ? nb : 31);
+      if (nb < 32) hi = first_after;
+      if (nb > 0) lo = last_before + 1;
+    }
+    const bool before = lo + lane < hi && ld_nc(runs + lo + lane).x <= key;
+    const int32_t r = lo + __popc(__ballot_sync(0xffffffffu, before));
+    if (lane == 0) out2[which] = r;
+  }
+}
+
+// ... and their copy, ends relative to start and clipped to the slice
+__global__ void k_slice_copy(const int2* runs, int32_t first, int32_t n, int32_t start, int32_t stop, int2* out) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int2 r = ld_nc(runs + first + i);
+    out[i] = make_int2((r.x < stop ? r.x : stop) - start, r.y);
+  }
+}
+
 // index[i] = end of run kIndexStride (i + 1) - 1  (see DSource::index)
 __global__ void k_build_index(const int2* runs, int32_t nruns, const int32_t* d_count, int32_t* index) {
   const int32_t n = d_count ? ld_nc(d_count) : nruns;
@@ -786,12 +817,13 @@ psk_status psk_store_from_runs_async(psk_dtype dtype, int64_t nruns, const int32
   // while they wait for PCIe and delay the persistent merge kernel.)
   unsigned char* tmp = nullptr;
   const size_t half = ((size_t)nruns * 4 + 15) & ~(size_t)15;
-  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&s->d_runs), (size_t)(nruns + kStorePad) * 8, g.h2d);
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&s->d_runs), store_bytes(nruns), g.h2d);
   if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&tmp), 2 * half, g.h2d);
   if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, ends, (size_t)nruns * 4, cudaMemcpyHostToDevice, g.h2d);
   if (e == cudaSuccess) e = cudaMemcpyAsync(tmp + half, vals, (size_t)nruns * 4, cudaMemcpyHostToDevice, g.h2d);
   if (e == cudaSuccess) {
     s->d_count = reinterpret_cast<int32_t*>(s->d_runs + nruns + kStorePad - 1);
+    s->d_index = reinterpret_cast<int32_t*>(s->d_runs + nruns + kStorePad);
     launch_interleave(s, reinterpret_cast<int32_t*>(tmp), tmp + half, nruns, g.d_async_err, g.h2d);
     e = cudaFreeAsync(tmp, g.h2d);
   }
@@ -1210,7 +1242,7 @@ psk_status eval_impl(int32_t k, const psk_source* sources, int32_t nprog, const 
       wait_ready(s.store);
       used_async = true;
     }
-    if (!s.store->indexed && d.nruns >= kIndexStride) {  // first use as a source: build the compact index
+    if (!s.store->indexed && s.store->d_index != nullptr && d.nruns >= kIndexStride) {  // first use as a source: build the compact index
       const int32_t entries = d.nruns / kIndexStride;
       LAUNCH(k_build_index, (unsigned)((entries + 255) / 256), 256, 0, (const int2*)s.store->d_runs, d.nruns,
              (const int32_t*)d.d_count, s.store->d_index);
@@ -1660,18 +1692,28 @@ psk_status psk_store_slice(psk_store_t s, int32_t start, int32_t stop, psk_store
   NEED_INIT();
   PSK_CHECK_ARG(s != nullptr && out != nullptr);
   PSK_CHECK_ARG(0 <= start && start < stop && stop <= s->span);
-  psk_source src;
-  memset(&src, 0, sizeof(src));
-  src.store = s;
-  src.nviews = 1;
-  src.views[0].kind = PSK_VIEW_GATHER;
-  src.views[0].ndim = 1;
-  src.views[0].shape[0] = s->span;
-  src.views[0].start[0] = start;
-  src.views[0].stop[0] = stop;
-  src.views[0].stride[0] = 1;
-  psk_node prog{PSK_OP_SRC, 0};
-  return psk_eval(1, &src, 1, &prog, (psk_dtype)s->dtype, PSK_EQ_BITWISE, out);
+  // (the same store as an evaluation through a one-dimensional gather view, without the
+  //  evaluation: two searches on the device, then a copy of exactly the runs that are needed)
+  READY(s);
+  int32_t* d_two = nullptr;
+  psk_status st = dmalloc(reinterpret_cast<void**>(&d_two), 8);
+  if (st != PSK_OK) return st;
+  LAUNCH(k_slice_find, 1, 32, 0, (const int2*)s->d_runs, (int32_t)s->nruns, start, stop, d_two);
+  cudaError_t e = cudaMemcpyAsync(g.h_ctrl, d_two, 8, cudaMemcpyDeviceToHost, g.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+  cudaFreeAsync(d_two, g.stream);
+  if (e != cudaSuccess) return fail(PSK_ECUDA, std::string("psk_store_slice: ") + cudaGetErrorString(e));
+  const int32_t first = g.h_ctrl[0], n = g.h_ctrl[1] - g.h_ctrl[0] + 1;
+  PSK_CHECK_STATE(n > 0 && first + n <= s->nruns);
+  psk_store_t res = nullptr;
+  st = new_store(s->dtype, n, &res);
+  if (st != PSK_OK) return st;
+  LAUNCH(k_slice_copy, (unsigned)((n + 255) / 256), 256, 0, (const int2*)s->d_runs, first, n, start, stop, res->d_runs);
+  LAUNCH(k_seal, 1, 32, 0, res->d_runs, n, res->d_count);
+  res->nruns = n;
+  res->span = stop - start;
+  *out = res;
+  return PSK_OK;
 }
 
 }  // extern "C"

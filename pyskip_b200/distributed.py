@@ -270,6 +270,32 @@ class ShardedTensor:
 
 # ---- z-slab convolution with halo exchange ------------------------------------------------
 
+# Development aid (PSKB200_DIST_PROFILE=1): wall time per stage of the slab convolution, each
+# stage closed by a device synchronisation; read with distributed.stage_times().
+_STAGES = {}
+
+
+def _stage(name, t0):
+    import os
+    import time
+    if os.environ.get("PSKB200_DIST_PROFILE") != "1":
+        return t0
+    import torch
+    _lib().synchronize()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    _STAGES[name] = _STAGES.get(name, 0.0) + (t1 - t0)
+    return t1
+
+
+def stage_times(reset=True):
+    out = dict(_STAGES)
+    if reset:
+        _STAGES.clear()
+    return out
+
+
 def exchange_halo(store, plane: int, span: int, dtype, fill):
     """Boundary z-slices of a slab as stores: -> (slice of rank-1, slice of rank+1), each of
     `plane` elements; edge ranks get the fill value.  The lowest / highest slice of `store`
@@ -284,8 +310,11 @@ def exchange_halo(store, plane: int, span: int, dtype, fill):
     fill_store = lambda: lib.store_fill(adt, plane, dtype(fill))
     if size == 1:
         return fill_store(), fill_store()
+    import time
+    t_ = time.perf_counter()
     lo = lib.store_slice(store, 0, plane) if rank > 0 else None
     hi = lib.store_slice(store, span - plane, span) if rank < size - 1 else None
+    t_ = _stage("halo: slice", t_)
     # 1) run counts to the neighbours
     cnt_send = torch.tensor([lo.nruns if lo else 0, hi.nruns if hi else 0], dtype=torch.int64, device=dev)
     cnt_recv = torch.zeros(2, dtype=torch.int64, device=dev)      # [from rank-1, from rank+1]
@@ -297,6 +326,7 @@ def exchange_halo(store, plane: int, span: int, dtype, fill):
     for req in dist.batch_isend_irecv(ops):
         req.wait()
     n_lo, n_hi = (int(v) for v in cnt_recv.cpu().numpy())
+    t_ = _stage("halo: counts", t_)
     # 2) exactly that many pairs
     bufs, ops = {}, []
     if rank > 0:
@@ -313,8 +343,10 @@ def exchange_halo(store, plane: int, span: int, dtype, fill):
         lib.synchronize()               # (CPU tests: the export is a plain memcpy)
     for req in dist.batch_isend_irecv(ops):
         req.wait()
+    t_ = _stage("halo: pairs", t_)
     below = lib.store_from_device_pairs(adt, n_lo, bufs["r_lo"].data_ptr()) if rank > 0 else fill_store()
     above = lib.store_from_device_pairs(adt, n_hi, bufs["r_hi"].data_ptr()) if rank < size - 1 else fill_store()
+    _stage("halo: adopt", t_)
     return below, above
 
 
@@ -337,9 +369,17 @@ def conv_3d_slab(local: Tensor, kernel: Tensor, padding=0, fill=0):
     dtype = local.dtype
     store = _handle(local)
     plane = X * Y
+    import time
+    t_ = time.perf_counter()
     below, above = exchange_halo(store, plane, plane * Z, dtype, fill)
+    t_ = time.perf_counter()
     ext = lib.store_concat([below, store, above])            # (X, Y, Z + 2), halos in place of z-padding
+    t_ = _stage("concat", t_)
     weights = np.ascontiguousarray(kernel.to_numpy()).astype(_NP_OF[dtype]).ravel()
+    t_ = _stage("kernel weights", t_)
     out = lib.conv_nd(ext, (X, Y, Z + 2), (3, 3, 3), weights, (px, py, 0),
                       _abi.value_bits(dtype(fill), _ABI_DTYPE[dtype]))
-    return _adopt(out, (X + 2 * px - 2, Y + 2 * py - 2, Z), dtype)
+    t_ = _stage("conv_nd", t_)
+    res = _adopt(out, (X + 2 * px - 2, Y + 2 * py - 2, Z), dtype)
+    _stage("adopt", t_)
+    return res

@@ -384,3 +384,25 @@ def test_streaming_conversion_of_a_long_buffer(lib):
     y = np.arange(3_000_000, dtype=np.int32)
     s = lib.store_from_dense(y)
     assert s.nruns == y.size and np.array_equal(s.to_dense(), y)
+
+
+def test_overlapped_transfers_match_the_synchronous_path(lib):
+    """psk_store_from_runs_async -> psk_eval -> psk_store_runs_async (what bench.py's e2e leg
+    does every step): stores uploaded on the copy stream are sources of an evaluation right
+    away, the result is downloaded on the second copy stream; same runs as the blocking calls."""
+    rng = np.random.default_rng(83)
+    n = 40_000 if lib.is_simulator() else 3_000_000
+    ops = [rand_runs(rng, n, n // 9, dtype=np.float32) for _ in range(3)]
+    expr = ("sub", ("mul", ("src", 0), ("src", 1)), ("src", 2))
+    want_e, want_v = run_eval(lib, [(e, v, []) for e, v in ops], expr)
+    from helpers import lower
+    abi_prog, _, _ = lower(expr, [np.float32] * 3)
+    for _ in range(2):
+        up = [lib.store_from_runs_async(e, v) for e, v in ops]
+        r = lib.eval([(s, []) for s in up], abi_prog, A.F32, A.EQ_BITWISE)
+        oe = np.empty(r.nruns, np.int32)
+        ov = np.empty(r.nruns, np.float32)
+        lib.store_runs_async(r, oe, ov)
+        lib.copy_synchronize()
+        lib.synchronize()
+        assert_runs_equal((oe, ov), (want_e, want_v), "async path")

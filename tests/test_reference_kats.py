@@ -42,6 +42,28 @@ def test_pool_partition_kat(lib):
             assert list(v) == list(want[lo:hi])
 
 
+def test_store_slice_matches_a_gather_view(lib):
+    """psk_store_slice (two searches + a copy on the device) gives the store an evaluation through
+    a one-dimensional gather view [start, stop) gives: random stores, cuts on and off run ends."""
+    rng = np.random.default_rng(91)
+    for n, r in ((1, 1), (40, 7), (5000, 900), (100_000, 3000)):
+        ends = np.sort(rng.choice(np.arange(1, n), size=min(r, n) - 1, replace=False)).astype(np.int32) if n > 1 else np.zeros(0, np.int32)
+        ends = np.append(ends, np.int32(n))
+        vals = np.arange(ends.size, dtype=np.int32) % 97
+        vals[1:][vals[1:] == vals[:-1]] += 1
+        s = lib.store_from_runs(ends, vals)
+        cuts = [(0, n), (0, 1), (n - 1, n)] + [tuple(sorted(rng.choice(n + 1, size=2, replace=False))) for _ in range(12)]
+        cuts += [(int(ends[len(ends) // 2]) - 1, n)] if ends.size > 1 and ends[len(ends) // 2] > 1 else []
+        for a, b in cuts:
+            a, b = int(a), int(b)
+            if a >= b:
+                continue
+            ge, gv = lib.store_slice(s, a, b).runs()
+            view = [("gather", (n,), [(a, b, 1)])]
+            we, wv = oracle_eval([(ends, vals, view)], ("src", 0))
+            assert_runs_equal((ge, gv), (we, wv), f"slice [{a}, {b}) of {n}")
+
+
 def _step_table(lib, views, span_in, args):
     """f(E) for every E in args: the end of run E of an all-distinct store of span_in elements,
     pushed through the view chain, is where that run ends in the output (0 when it vanishes)."""
