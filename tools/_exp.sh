@@ -1,3 +1,1 @@
-for d in "-DPSK_COARSE_GROUP=8" "-DPSK_COARSE_GROUP=4" "-DPSK_COARSE_GROUP=2"; do
-  echo "== $d"; PSKB200_JIT_DEFS=$d timeout 200 python tools/sweep_geom.py --geoms 256x4096x2 2>&1 | tail -1 | cut -c1-100
-done
+PSKB200_PRINT_CTRL3=1 PSKB200_JIT_DEFS="-DPSK_COUNT_DIRECT" timeout 200 python tools/sweep_geom.py --reps 3 --geoms 256x4096x2,256x4096x1 2>&1 | tail -12 | cut -c1-100
