@@ -25,13 +25,15 @@ D.use_torch_stream()
 ends, vals = bench.slab_columns(rank, 2048, 2048, ZL)
 t = ps.Tensor(shape=(2048, 2048, ZL), val=E.IntArray._from_runs(ends, vals))
 k = ps.Tensor.from_numpy(np.random.default_rng(3001).integers(0, 8, size=(3, 3, 3)).astype(np.int32))
-for i in range(4):
+for i in range(6):
     E.synchronize(); torch.cuda.synchronize(); dist.barrier()
     t0 = time.perf_counter()
     out = D.conv_3d_slab(t, k, padding=1, fill=0)
     E.synchronize(); torch.cuda.synchronize(); dist.barrier()
     dt = time.perf_counter() - t0
     st = D.stage_times()
-    if rank == 0:
-        print(f"iter {i}: {dt * 1e3:.2f} ms; " + "; ".join(f"{k_} {v * 1e3:.2f}" for k_, v in st.items()))
+    for r in range(dist.get_world_size()):
+        if r == rank and i >= 3:
+            print(f"rank {rank} iter {i}: {dt * 1e3:.2f} ms; " + "; ".join(f"{k_} {v * 1e3:.2f}" for k_, v in st.items()), flush=True)
+        dist.barrier()
 dist.destroy_process_group()
