@@ -1522,8 +1522,14 @@ psk_status psk_conv_nd(psk_store_t s, int32_t ndim, const int32_t* shape, const 
   // every output row sees, per tap, the pieces of one input row: its runs + two padding pieces
   const int64_t in_rows = (int64_t)ext[1] * ext[2];
   const int64_t out_rows = (int64_t)oext[1] * oext[2];
-  int64_t cap = (int64_t)taps * ((int64_t)cp.nruns + 3 * in_rows) + 2 * out_rows;
-  if (cap > n_out) cap = n_out;
+  // worst case: every tap contributes all of its pieces to every output row
+  int64_t cap_full = (int64_t)taps * ((int64_t)cp.nruns + 3 * in_rows) + 2 * out_rows;
+  if (cap_full > n_out) cap_full = n_out;
+  // Voxel data stays far below that (BASELINE configs 3 / 4: 4.5x / 8.2x the input runs), so the
+  // output is first sized for 12 runs per input piece; the kernel counts every run even when it
+  // cannot write them all, and a second pass with the exact size follows in that (dense) case.
+  int64_t cap = 12 * ((int64_t)cp.nruns + in_rows) + 2 * out_rows;
+  if (cap > cap_full) cap = cap_full;
   const int64_t n_tiles = (out_rows + kConvRowThreads - 1) / kConvRowThreads;
   // scratch: [tile_state | ctrl | row_start]
   const size_t o_ctrl = (size_t)n_tiles * 8 * kStateStride;
@@ -1531,39 +1537,48 @@ psk_status psk_conv_nd(psk_store_t s, int32_t ndim, const int32_t* shape, const 
   unsigned char* scratch = nullptr;
   psk_status st = dmalloc(reinterpret_cast<void**>(&scratch), o_rows + (size_t)in_rows * 4);
   if (st != PSK_OK) return st;
-  psk_store_t res = nullptr;
-  st = new_store(s->dtype, cap, &res);
-  if (st != PSK_OK) {
-    cudaFreeAsync(scratch, g.stream);
-    return st;
-  }
   cp.tile_state = reinterpret_cast<unsigned long long*>(scratch);
   cp.ctrl = reinterpret_cast<int32_t*>(scratch + o_ctrl);
   cp.row_start = reinterpret_cast<int32_t*>(scratch + o_rows);
-  cp.out = res->d_runs;
-  cp.out_capacity = (int32_t)cap;
-  cp.out_count = res->d_count;
-  cudaError_t e = cudaMemsetAsync(scratch, 0, o_rows, g.stream);
-  if (e == cudaSuccess) {
-    LAUNCH(k_conv_row_starts, (unsigned)((in_rows + 255) / 256), 256, 0, cp);
-    const bool is_f = s->dtype == PSK_F32;
-    if (g.profile) cudaEventRecord(g.pev0, g.stream);
-    if (ndim == 3) launch_conv<3, 3, 3>(is_f, (unsigned)n_tiles, cp);
-    else launch_conv<3, 3, 1>(is_f, (unsigned)n_tiles, cp);
-    if (g.profile) cudaEventRecord(g.pev1, g.stream);
-    e = cudaGetLastError();
+  psk_store_t res = nullptr;
+  for (int pass = 0; pass < 2; ++pass) {
+    st = new_store(s->dtype, cap, &res);
+    if (st != PSK_OK) {
+      cudaFreeAsync(scratch, g.stream);
+      return st;
+    }
+    cp.out = res->d_runs;
+    cp.out_capacity = (int32_t)cap;
+    cp.out_count = res->d_count;
+    cudaError_t e = cudaMemsetAsync(scratch, 0, o_rows, g.stream);
+    if (e == cudaSuccess) {
+      if (pass == 0) LAUNCH(k_conv_row_starts, (unsigned)((in_rows + 255) / 256), 256, 0, cp);
+      const bool is_f = s->dtype == PSK_F32;
+      if (g.profile) cudaEventRecord(g.pev0, g.stream);
+      if (ndim == 3) launch_conv<3, 3, 3>(is_f, (unsigned)n_tiles, cp);
+      else launch_conv<3, 3, 1>(is_f, (unsigned)n_tiles, cp);
+      if (g.profile) cudaEventRecord(g.pev1, g.stream);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(g.h_ctrl, cp.ctrl, CTRL_WORDS * 4, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) {
+      cudaFreeAsync(scratch, g.stream);
+      psk_store_release(res);
+      return fail(PSK_ECUDA, std::string("psk_conv_nd: ") + cudaGetErrorString(e));
+    }
+    if (g.h_ctrl[CTRL_ERROR] == 0) break;
+    // did not fit: the count is exact, repeat with it
+    psk_store_release(res);
+    res = nullptr;
+    const int64_t need = g.h_ctrl[CTRL_COUNT];
+    if (pass == 1 || need <= cap || need > cap_full) {
+      cudaFreeAsync(scratch, g.stream);
+      return fail(PSK_ESTATE, "psk_conv_nd: output capacity exceeded (internal bound violated)");
+    }
+    cap = need;
   }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(g.h_ctrl, cp.ctrl, CTRL_WORDS * 4, cudaMemcpyDeviceToHost, g.stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
   cudaFreeAsync(scratch, g.stream);
-  if (e != cudaSuccess) {
-    psk_store_release(res);
-    return fail(PSK_ECUDA, std::string("psk_conv_nd: ") + cudaGetErrorString(e));
-  }
-  if (g.h_ctrl[CTRL_ERROR] != 0) {
-    psk_store_release(res);
-    return fail(PSK_ESTATE, "psk_conv_nd: output capacity exceeded (internal bound violated)");
-  }
   res->nruns = g.h_ctrl[CTRL_COUNT];
   res->span = (int32_t)n_out;
   if (g.profile) {  // the stencil kernel is this entry point's dominant kernel

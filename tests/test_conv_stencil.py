@@ -93,3 +93,25 @@ def test_conv_stencil_float_signed_zero_and_order(api):
     t, k = ps.Tensor.from_numpy(vol), ps.Tensor.from_numpy(ker)
     a, b = _both(ps, lambda: ps.functional.conv_3d(t, k, padding=1, fill=-0.0))
     _same_runs(a, b, True)
+
+
+def test_conv3d_output_larger_than_the_first_guess(api):
+    """psk_conv_nd sizes its output for 12 runs per input piece first; isolated voxels at staggered
+    positions in neighbouring rows give ~14 output runs per input run, so the first pass only
+    counts and a second pass with the exact size writes (same result as the tap loop and the
+    dense oracle)."""
+    ps, E = api
+    X, Y, Z = 1024, 12, 12
+    vol = np.zeros((Z, Y, X), np.int32)
+    for z in range(Z):
+        for y in range(Y):
+            off = 3 * ((y % 3) + 3 * (z % 3))      # the 27 products of 9 neighbouring rows never overlap
+            vol[z, y, 8 + off:X - 40:40] = 1 + (np.arange(len(range(8 + off, X - 40, 40))) % 5)
+    ker = (np.arange(27, dtype=np.int32).reshape(3, 3, 3) * 7 + 1) % 23 + 1
+    t, k = ps.Tensor.from_numpy(vol), ps.Tensor.from_numpy(ker)
+    n_in = t.rle_length()
+    a, b = _both(ps, lambda: ps.functional.conv_3d(t, k, padding=1, fill=0))
+    _same_runs(a, b)
+    assert np.array_equal(a.to_numpy(), O.conv3d_dense(vol, ker, padding=1, fill=0))
+    rows = Y * Z
+    assert a.rle_length() > 12 * (n_in + rows) + 2 * rows, (a.rle_length(), n_in)   # the case this test is about
