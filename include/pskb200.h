@@ -250,7 +250,9 @@ PSK_API int32_t psk_store_span(psk_store_t s);
 PSK_API int32_t psk_store_pending(psk_store_t s);
 PSK_API int32_t psk_store_dtype(psk_store_t s);
 /* Device pointer of the run array (valid while the store is alive): nruns pairs of
- * { int32 end; uint32 payload }, followed by two sentinel pairs (end = INT32_MAX). */
+ * { int32 end; uint32 payload }, followed by two sentinel pairs (end = INT32_MAX).  (Behind the
+ * padding the same allocation holds the store's compact index -- the ends of every 16th run,
+ * filled on first use as a source of psk_eval -- which is private to the library.) */
 PSK_API psk_status psk_store_device_pairs(psk_store_t s, const void** d_pairs);
 /* The payload of run 0 (used for 1-run stores, i.e. scalars). */
 PSK_API psk_status psk_store_first_value(psk_store_t s, uint32_t* bits);
@@ -321,7 +323,8 @@ PSK_API psk_status psk_store_boundary(psk_store_t s, uint32_t* first_bits, uint3
 /* Same triple written as 3 x int64 into DEVICE memory on the library stream (no host sync):
  * the send buffer of the all-gather. */
 PSK_API psk_status psk_store_boundary_device(psk_store_t s, int64_t* d_out3);
-/* Sub-range [start, stop) of a store re-based to 0 (SimpleSource::split, eval.hpp:281-287). */
+/* Sub-range [start, stop) of a store re-based to 0 (SimpleSource::split, eval.hpp:281-287):
+ * two searches on the device and a copy of the runs that cover the range. */
 PSK_API psk_status psk_store_slice(psk_store_t s, int32_t start, int32_t stop, psk_store_t* out);
 #endif /* !__CUDACC_RTC__ */
 
